@@ -1,0 +1,172 @@
+/*
+ * tt_b200.h -- C ABI of libtt_b200.so: the B200 (sm_100a) implementation of the
+ * ray-integration hot path of jdhare/turbulence_tracing.
+ *
+ * The reference has no FFI of its own (it is pure Python); each entry point
+ * below names the reference function it replaces (paths relative to the reference checkout).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every *_dev pointer is DEVICE memory owned by the caller,
+ *     every other pointer is HOST memory.  The library allocates nothing persistent: scratch
+ *     space is passed in after a *_workspace() size query.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); entry points that return
+ *     device results do not synchronise.  The *_host convenience entry points (host buffers
+ *     in and out) synchronise before returning.
+ *   - return value: TT_OK or an error code; tt_last_error() gives the thread-local message.
+ *     No exceptions cross the ABI.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point returns TT_ERR_CUDA.
+ *   - frame order: a cube with probing axis `par` (0=x, 1=y, 2=z) is stored in the ray frame
+ *     (u, v, w) = (t1, t2, par) with (t1, t2) the transverse axes in the reference's `rf`
+ *     order: par=z -> (x, y), par=y -> (x, z), par=x -> (y, z)   (particle_tracker.py:353-378).
+ *     Gradient grid layout: grid[iw][iv][iu] of 4-vectors (g_u, g_v, g_w, ne/nc) with
+ *     g = -1/2 * d(ne/nc)/d(coordinate) in 1/m, i.e. the reference's dndx/c^2
+ *     (particle_tracker.py:235-237); 16 B per voxel in TT_F32, 32 B in TT_F64.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_B200_ABI_VERSION 1
+
+enum { TT_F32 = 0, TT_F64 = 1 };
+enum { TT_OK = 0, TT_ERR_INVALID = 1, TT_ERR_CUDA = 2, TT_ERR_UNSUPPORTED = 3 };
+
+/* per-ray status written by tt_trace (bit flags) */
+enum {
+    TT_RAY_EXIT_FACE = 1,  /* left through the far face of the probing axis               */
+    TT_RAY_EXIT_SIDE = 2,  /* left through another face                                   */
+    TT_RAY_TIME_CAP = 4,   /* still inside at c*T = s_max (particle_tracker.py:317)       */
+    TT_RAY_MISSED = 8,     /* never entered the cube                                      */
+    TT_RAY_GENERAL = 16    /* left the plane-marching fast path (steep or backward ray)   */
+};
+
+typedef void* tt_stream_t;
+
+int tt_abi_version(void);
+const char* tt_last_error(void);
+/* number of CUDA devices visible, or -1 with tt_last_error() set */
+int tt_device_count(void);
+
+/* ---- K1: ElectronCube.calc_dndr (particle_tracker.py:220-241) ------------------------------
+ * ne_dev: the reference's C-ordered cube ne[ix][iy][iz], float (TT_F32) or double (TT_F64).
+ * n_xyz / spacing_xyz: points and (uniform) node spacing per axis.  nc = critical density,
+ * ne_max = clip of ne/nc (:231).  Differences follow numpy.gradient: central inside,
+ * first-order one-sided on the faces (:235-237).  Output: frame-ordered grid (see top).      */
+int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3],
+                 const double spacing_xyz[3], int par, double nc, double ne_max,
+                 void* grid4_dev, int grid_dtype, tt_stream_t stream);
+
+/* ---- ElectronCube.dndr (particle_tracker.py:243-256) ----------------------------------------
+ * Trilinear gradient at npts positions pos_dev[3][npts] (x, y, z rows, metres); zero outside
+ * the cube, faces inclusive.  out_dev[3][npts] in the reference's units (m/s^2, = c^2 * g).   */
+int tt_dndr(const void* grid4_dev, int grid_dtype, const int n_xyz[3], const double origin_xyz[3],
+            const double spacing_xyz[3], int par, const double* pos_dev, long npts,
+            double* out_dev, tt_stream_t stream);
+
+/* ---- ElectronCube.init_beam (particle_tracker.py:258-310), device RNG variant ---------------
+ * Same distribution and draw semantics (uniform disc radius beam_size via folded sum of two
+ * uniforms, azimuth in [0, pi), Gaussian divergence), Philox4x32-10 counter RNG keyed by
+ * (seed, first_ray + i) so that any shard of a beam can be generated on any rank.
+ * s0_dev[6][np] rows x, y, z, vx, vy, vz (m, m/s).                                            */
+int tt_init_beam(long np, long first_ray, uint64_t seed, double beam_size, double divergence,
+                 double extent, int par, double* s0_dev, tt_stream_t stream);
+
+/* ---- Morton order of launch positions (locality for the gather; no reference equivalent) ---
+ * perm_dev[i] = index of the i-th ray along a Z-order curve over the transverse launch
+ * position.  Workspace from tt_sort_rays_workspace().                                         */
+int tt_sort_rays_workspace(long np, size_t* bytes);
+int tt_sort_rays(const double* s0_dev, long np, int par, const double origin_xyz[3],
+                 const double spacing_xyz[3], const int n_xyz[3], uint32_t* perm_dev,
+                 void* workspace_dev, size_t workspace_bytes, tt_stream_t stream);
+
+/* ---- K3+K4: ElectronCube.solve + dsdt + ray_at_exit (particle_tracker.py:312-331, 398-419,
+ *      333-380) --------------------------------------------------------------------------------
+ * Fixed-step RK4, marching plane to plane along the probing axis (steps_per_cell sub-planes
+ * per cell), trilinear gradient with zero outside the cube, rays frozen when they leave, path
+ * time capped at s_max = c*T = sqrt(8)*extent.  rf_dev[4][np] = (p1, atan(v1/vpar), p2,
+ * atan(v2/vpar)) on the plane par-axis = +extent, SAME ray order as s0 (perm only changes
+ * which thread integrates which ray).  sf_dev[6][np] (nullable) = state at time T as the
+ * reference's cube.sf.  ray_steps_dev (nullable) is incremented by the number of RK4 steps
+ * taken inside the cube.  status_dev[np] (nullable) receives TT_RAY_* flags.                  */
+typedef struct tt_trace_params {
+    int n_xyz[3];
+    double origin_xyz[3];   /* coordinate of node 0 per axis (m)            */
+    double spacing_xyz[3];  /* uniform node spacing per axis (m)            */
+    int par;                /* probing axis 0/1/2                            */
+    double extent;          /* exit plane = +extent, launch plane = -extent */
+    double s_max;           /* c*T                                           */
+    int steps_per_cell;     /* >= 1                                          */
+    int dtype;              /* TT_F32 or TT_F64: grid element type and state arithmetic */
+    int variant;            /* 0 = default kernel; others select experimental kernels  */
+} tt_trace_params;
+
+int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_dev, long np,
+             const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
+             unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
+
+/* ---- K5+K6: ray_transfer_matrix.py optics (:37-154), detector programs (:208-299) and
+ *      Rays.histogram (:173-195) ---------------------------------------------------------------
+ * One pass over the rays: scale positions (pos_scale = 1e3 is m_to_mm, :37-40), run the element
+ * program, bin the survivors like numpy.histogram2d (right-open bins, last edge inclusive,
+ * NaN dropped), H_dev[nby][nbx] (already transposed as :191) accumulated as uint64 counts.
+ * rf_out_dev[4][np] nullable.  Rejected rays are NaN in all four rows (:78).                   */
+enum {
+    TT_OP_DISTANCE = 0,      /* a = d                          distance()          :62-71   */
+    TT_OP_LENS = 1,          /* a = f1, b = f2                 lens()/sym_lens()   :42-60   */
+    TT_OP_CIRC_APERTURE = 2, /* a = R   reject r^2 >  R^2      circular_aperture() :73-79   */
+    TT_OP_CIRC_STOP = 3,     /* a = R   reject r^2 <  R^2      circular_stop()     :81-87   */
+    TT_OP_ANNULAR_STOP = 4,  /* a = R1, b = R2 reject between  annular_stop() as used by
+                                                               angular_filter()    :89-111  */
+    TT_OP_RECT_APERTURE = 5, /* a = Lx, b = Ly (both outside)  rect_aperture()     :128-136 */
+    TT_OP_KNIFE_EDGE = 6     /* a = offset, b = +-1 (x) or +-2 (y): sign = direction :138-154 */
+};
+typedef struct tt_optic {
+    int op;
+    int pad_;
+    double a, b;
+} tt_optic;
+
+#define TT_MAX_OPTICS 64
+
+int tt_optics_hist(const double* rf_in_dev, long np, double pos_scale, const tt_optic* program,
+                   int n_ops, const double* xedges_dev, int nbx, const double* yedges_dev, int nby,
+                   unsigned long long* H_dev, double* rf_out_dev, tt_stream_t stream);
+/* same, visiting the rays in the order perm_dev[0..np) (the Morton order of tt_sort_rays), so
+ * that a CTA's rays fall into a compact detector patch; rf_out keeps the original ray order. */
+int tt_optics_hist_perm(const double* rf_in_dev, long np, const uint32_t* perm_dev, double pos_scale,
+                        const tt_optic* program, int n_ops, const double* xedges_dev, int nbx,
+                        const double* yedges_dev, int nby, unsigned long long* H_dev,
+                        double* rf_out_dev, tt_stream_t stream);
+
+/* ---- K7: turboGen.gaussian3D_FFT (gaussian_fields/turboGen.py:488-538) -----------------------
+ * Hermitian spectrum shaping + inverse real FFT (cuFFT) on the odd grid M = 2N+1.
+ * sqrtP_lut_dev[3N^2+1]: sqrt(k_func(sqrt(q)/M)) for q = i^2+j^2+l^2 (the host evaluates the
+ * user's Python k_func once per distinct |k|).  Wr_dev/Wi_dev: the two N(0,1) cubes of
+ * :522-523 (M^3 doubles each) for bit-comparable runs, or both NULL to draw them from
+ * Philox(seed).  out_dev: M^3 reals (dtype), = ifftn(F).real of :536-538.  Workspace from
+ * tt_grf_workspace().                                                                          */
+int tt_grf_workspace(int N, int dtype, size_t* bytes);
+int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev,
+             const double* Wi_dev, uint64_t seed, void* out_dev, void* workspace_dev,
+             size_t workspace_bytes, tt_stream_t stream);
+
+/* ---- host-buffer convenience entry point (what a ctypes binding inside the reference calls) --
+ * Whole path for one bundle of rays with HOST arrays: ne (C order, double) -> gradient grid ->
+ * Morton sort -> trace -> rf (host, 4 x np doubles).  Allocates and frees its device scratch
+ * internally, synchronises.  Same numerics as the device entry points above.                   */
+int tt_solve_host(const double* ne_host, const int n_xyz[3], const double origin_xyz[3],
+                  const double spacing_xyz[3], int par, double nc, double ne_max, double extent,
+                  int steps_per_cell, int dtype, const double* s0_host, long np, double* rf_host,
+                  double* sf_host, unsigned long long* ray_steps_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */

@@ -1,0 +1,432 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures
+that were produced by the live reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star):
+  FP64 mode  : exit positions / angles within 1e-5, relative to the beam radius / rms angle
+  FP32 mode  : exit position within 1e-3 of a detector pixel (pixel = Lx/(pix_x//bin_scale)
+               = 18 mm / 344 = 52.3 um  ->  52 nm)
+  histograms : identical counts (rays are bit-identical inputs to the binning on both sides)
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+PIXEL_M = 18e-3 / (3448 // 10)          # detector pixel of the default histogram, in metres
+
+
+@pytest.fixture(scope="module")
+def tt():
+    import torch
+    assert torch.cuda.is_available()
+    import turbulence_tracing_b200 as pkg
+    from turbulence_tracing_b200 import _lib
+    lib = _lib.load(build_if_missing=False)     # the shipped .so must be the one that runs
+    assert lib.tt_device_count() >= 1
+    return pkg
+
+
+def _cube_from_golden(tt, g, dtype, spc, **kw):
+    pt = tt.particle_tracker
+    n = int(g["n"])
+    x = np.linspace(-5e-3, 5e-3, n)
+    if "kind" in g.files:
+        keys = [str(k) for k in g["kw_keys"]]
+        ne = orc.density(str(g["kind"]), x, x, x, **dict(zip(keys, [float(v) for v in g["kw_vals"]])))
+        d = str(g["direction"])
+    else:
+        ne, d = kw.pop("ne"), "z"
+    cube = pt.ElectronCube(x, x, x, probing_direction=d, dtype=dtype, steps_per_cell=spc, verbose=False)
+    cube.external_ne(ne)
+    cube.calc_dndr()
+    return cube
+
+
+def _errors(rf, ref, s0, par):
+    """position error in metres; angle error relative to the rms angle"""
+    pos = max(np.max(np.abs(rf[0] - ref[0])), np.max(np.abs(rf[2] - ref[2])))
+    arms = max(np.sqrt(np.mean(ref[1] ** 2 + ref[3] ** 2)), 1e-6)
+    ang = max(np.max(np.abs(rf[1] - ref[1])), np.max(np.abs(rf[3] - ref[3]))) / arms
+    return pos, ang
+
+
+# ------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 2e-7)])
+def test_calc_dndr_matches_reference(tt, golden, dtype, tol):
+    g = golden("calc_dndr_uniform")
+    pt = tt.particle_tracker
+    for d in "xyz":
+        cube = pt.ElectronCube(g["x"], g["x"], g["x"], probing_direction=d, dtype=dtype)
+        cube.external_ne(g["ne"])
+        cube.calc_dndr()
+        assert cube.omega == pytest.approx(orc.critical_density()[0], rel=1e-15)
+        for name in ("ne_nc", "dndx", "dndy", "dndz"):
+            ref = g[name]
+            np.testing.assert_allclose(getattr(cube, name), ref, rtol=0, atol=tol * np.abs(ref).max(),
+                                       err_msg=f"{name} dir={d}")
+
+
+def test_calc_dndr_clip_edges_and_float32_input(tt, golden):
+    g = golden("calc_dndr")          # non-cubic 12 x 10 x 14 cube, ne_max = 0.5, values above the clip
+    pt = tt.particle_tracker
+    x = np.linspace(g["x"][0], g["x"][-1], 12)
+    y = np.linspace(g["y"][0], g["y"][-1], 10)
+    z = np.linspace(g["z"][0], g["z"][-1], 14)
+    d = orc.calc_dndr(g["ne"], x, y, z, float(g["lwl"]), float(g["ne_max"]))
+    for dr in "xyz":
+        cube = pt.ElectronCube(x, y, z, probing_direction=dr, dtype="float64")
+        cube.external_ne(g["ne"])
+        cube.calc_dndr(lwl=float(g["lwl"]), ne_max=float(g["ne_max"]))
+        assert cube.ne_nc.max() == 0.5
+        for name in ("ne_nc", "dndx", "dndy", "dndz"):
+            np.testing.assert_allclose(getattr(cube, name), d[name], rtol=0, atol=1e-11 * np.abs(d[name]).max())
+        # ElectronCube.dndr / the dnd?_interp objects: faces inside, zero outside
+        got = cube.dndr(g["pts"])
+        np.testing.assert_allclose(got, g["dndr_at_pts"], rtol=0, atol=1e-10 * np.abs(g["dndr_at_pts"]).max())
+        assert np.all(got[:, np.abs(g["pts"][0]) > x[-1]] == 0)
+        np.testing.assert_allclose(cube.dndy_interp(g["pts"].T), g["dndr_at_pts"][1], rtol=0,
+                                   atol=1e-10 * np.abs(g["dndr_at_pts"]).max())
+    cube32 = pt.ElectronCube(x, y, z, dtype="float32")
+    cube32.external_ne(g["ne"].astype(np.float32))
+    cube32.calc_dndr(lwl=float(g["lwl"]), ne_max=float(g["ne_max"]))
+    np.testing.assert_allclose(cube32.dndx, d["dndx"], rtol=0, atol=1e-5 * np.abs(d["dndx"]).max())
+
+
+def test_nonuniform_axis_raises(tt):
+    pt = tt.particle_tracker
+    x = np.linspace(-1e-3, 1e-3, 9)
+    xb = x.copy()
+    xb[3] += 1e-5
+    cube = pt.ElectronCube(xb, x, x)
+    cube.external_ne(np.zeros((9, 9, 9)))
+    with pytest.raises(NotImplementedError):
+        cube.calc_dndr()
+
+
+# ------------------------------------------------------------------------------------------- K3/K4
+TRACES = sorted(glob.glob(os.path.join(GOLDEN, "trace_[0-9]_*.npz")))
+
+
+@pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[:-4] for p in TRACES])
+def test_trace_fp64_matches_reference(tt, path):
+    g = np.load(path)
+    cube = _cube_from_golden(tt, g, "float64", 8)
+    cube.s0 = g["s0"]
+    cube.extent = float(g["extent"])
+    rf = np.asarray(cube.solve())
+    par = "xyz".index(str(g["direction"]))
+    pos, ang = _errors(rf, g["rf"], g["s0"], par)
+    beam = max(np.abs(g["s0"][[a for a in range(3) if a != par]]).max(), 1e-4)
+    print(f"{os.path.basename(path)}: pos err {pos:.3e} m ({pos / beam:.2e} of beam), angle err {ang:.2e} of rms")
+    assert pos / beam <= 1e-5
+    assert ang <= 1e-5
+    # cube.sf: state at time T, as the reference stores it
+    sf = np.asarray(cube.sf)
+    np.testing.assert_allclose(sf[:3], g["sf"][:3], rtol=0, atol=1e-5 * beam)
+    np.testing.assert_allclose(sf[3:], g["sf"][3:], rtol=0, atol=1e-5 * np.abs(g["sf"][3:]).max())
+    # ray_at_exit() recomputed from sf agrees with the kernel epilogue
+    np.testing.assert_allclose(np.asarray(cube.ray_at_exit()), rf, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("path", TRACES, ids=[os.path.basename(p)[:-4] for p in TRACES])
+def test_trace_fp32_within_pixel_tolerance(tt, path):
+    g = np.load(path)
+    spc = 4 if int(g["n"]) < 64 else 1        # coarse fixtures: h is 16x the 513-cube cell
+    cube = _cube_from_golden(tt, g, "float32", spc)
+    cube.s0 = g["s0"]
+    cube.extent = float(g["extent"])
+    rf = np.asarray(cube.solve())
+    pos, ang = _errors(rf, g["rf"], g["s0"], 2)
+    print(f"{os.path.basename(path)} fp32 spc={spc}: pos err {pos:.3e} m = {pos / PIXEL_M:.2e} pixel, angle {ang:.2e}")
+    assert pos <= 1e-3 * PIXEL_M
+
+
+def test_trace_grf_convergence_and_modes(tt, golden):
+    """k^-11/3 random cube (33^3): FP64 converges to the tight-tolerance reference at 2nd order;
+    FP32 at the same step agrees with FP64 to rounding; sorted == unsorted bit for bit."""
+    g = golden("trace_grf33")
+    pt = tt.particle_tracker
+    errs = {}
+    for spc in (1, 2, 4, 8):
+        cube = pt.ElectronCube(g["x"], g["x"], g["x"], dtype="float64", steps_per_cell=spc, verbose=False)
+        cube.external_ne(g["ne"])
+        cube.calc_dndr()
+        cube.s0 = g["s0"]
+        cube.extent = float(g["extent"])
+        rf = np.asarray(cube.solve())
+        errs[spc] = _errors(rf, g["rf"], g["s0"], 2)
+        if spc == 4:
+            rf4 = rf
+            cube.sort_rays = False
+            np.testing.assert_array_equal(np.asarray(cube.solve()), rf4)
+            assert cube.ray_steps == 32 * 4 * g["s0"].shape[1]
+    print("grf33 fp64 (pos m, angle/rms) by steps_per_cell:", errs)
+    assert errs[8][0] <= 1e-5 * 4e-3 and errs[8][1] <= 1e-5
+    assert errs[8][1] < errs[2][1] / 4          # at least ~2nd order
+    cube = pt.ElectronCube(g["x"], g["x"], g["x"], dtype="float32", steps_per_cell=4, verbose=False)
+    cube.external_ne(g["ne"])
+    cube.calc_dndr()
+    cube.s0 = g["s0"]
+    cube.extent = float(g["extent"])
+    rf32 = np.asarray(cube.solve())
+    pos = max(np.abs(rf32[0] - rf4[0]).max(), np.abs(rf32[2] - rf4[2]).max())
+    print(f"grf33 fp32 vs fp64 at spc=4: {pos:.3e} m = {pos / PIXEL_M:.2e} pixel")
+    assert pos <= 1e-3 * PIXEL_M
+
+
+def test_trace_liner_over_critical(tt, golden):
+    """ne > nc: ne/nc clipped at ne_max, rays deflected by up to 90 degrees (notebook cells 21-27).
+    Rays with |angle| <= 0.5 rad must match; steep ones only have to come out finite."""
+    g = golden("trace_liner")
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, int(g["n"]))
+    cube = pt.ElectronCube(x, x, x, dtype="float64", steps_per_cell=16, verbose=False)
+    cube.external_ne(orc.density("liner", x, x, x, n_e0=2e27, LR=1e-3))
+    cube.calc_dndr()
+    cube.s0 = g["s0"]
+    cube.extent = float(g["extent"])
+    rf = np.asarray(cube.solve(return_status=True))
+    assert np.all(np.isfinite(rf))
+    ok = (np.abs(g["rf"][1]) <= 0.5) & (np.abs(g["rf"][3]) <= 0.5)
+    assert ok.sum() >= 8
+    np.testing.assert_allclose(rf[1][ok], g["rf"][1][ok], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(rf[0][ok], g["rf"][0][ok], rtol=0, atol=2e-6)
+
+
+def test_rays_outside_and_edge_cases(tt):
+    """Rays that miss the cube, start outside it, sit on faces, or leave through a side face."""
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 21)
+    ne = orc.density("slab", x, x, x, s=8, n_e0=1e25)
+    field = orc.make_field(ne, x, x, x)
+    c0 = orc.C_LIGHT
+    s0 = np.zeros((6, 6))
+    s0[5] = c0
+    s0[2] = -5e-3
+    s0[0, 0] = 7e-3                                   # misses the cube entirely
+    s0[0, 1], s0[3, 1] = -6e-3, 0.2 * c0              # starts outside, enters through a side face
+    s0[5, 1] = np.sqrt(1 - 0.04) * c0
+    s0[0, 2], s0[3, 2] = 4.9e-3, 0.1 * c0             # leaves through the +x side face
+    s0[2, 3] = -8e-3                                  # starts in front of the cube
+    s0[0, 4] = 5e-3                                   # runs along the x = +extent face
+    s0[1, 5] = -5e-3                                  # on an edge
+    rf_ref, sf_ref, _ = orc.solve(field, s0, 5e-3, "z", rtol=1e-10, atol=1e-13, batch=1)
+    cube = pt.ElectronCube(x, x, x, dtype="float64", steps_per_cell=8, verbose=False)
+    cube.external_ne(ne)
+    cube.calc_dndr()
+    cube.s0 = s0
+    cube.extent = 5e-3
+    rf = np.asarray(cube.solve(return_status=True))
+    st = np.asarray(cube.status)
+    assert st[0] & 8 and st[2] & 2 and st[3] & 1
+    np.testing.assert_allclose(rf[1], rf_ref[1], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(rf[0], rf_ref[0], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(np.asarray(cube.sf)[:3], sf_ref[:3], rtol=0, atol=5e-8)
+    # empty bundle
+    cube.s0 = np.zeros((6, 0))
+    assert np.asarray(cube.solve()).shape == (4, 0)
+
+
+def test_solve_host_c_abi(tt, golden):
+    """tt_solve_host: the host-buffer entry point a ctypes binding inside the reference would call."""
+    from turbulence_tracing_b200 import _lib
+    lib = _lib.load()
+    g = golden("trace_grf33")
+    x = g["x"]
+    n = len(x)
+    ne = np.ascontiguousarray(g["ne"], dtype=np.float64)
+    s0 = np.ascontiguousarray(g["s0"], dtype=np.float64)
+    npr = s0.shape[1]
+    rf = np.empty((4, npr))
+    sf = np.empty((6, npr))
+    steps = C.c_ulonglong(0)
+    h = (x[-1] - x[0]) / (n - 1)
+    rc = lib.tt_solve_host(ne.ctypes.data, _lib.i3((n, n, n)), _lib.d3((x[0],) * 3), _lib.d3((h,) * 3), 2,
+                           orc.critical_density()[1], 1.0, float(g["extent"]), 8, _lib.TT_F64,
+                           s0.ctypes.data, npr, rf.ctypes.data, sf.ctypes.data, C.byref(steps))
+    assert rc == 0, lib.tt_last_error()
+    pos, ang = _errors(rf, g["rf"], s0, 2)
+    assert pos <= 1e-5 * 4e-3 and ang <= 1e-5
+    assert steps.value == 32 * 8 * npr
+    # error path: bad dtype is reported, not thrown
+    rc = lib.tt_solve_host(ne.ctypes.data, _lib.i3((n, n, n)), _lib.d3((x[0],) * 3), _lib.d3((h,) * 3), 2,
+                           1e27, 1.0, 5e-3, 8, 7, s0.ctypes.data, npr, rf.ctypes.data, None, None)
+    assert rc == 1 and b"dtype" in lib.tt_last_error()
+
+
+# ------------------------------------------------------------------------------------------- beam
+def test_init_beam_host_is_bit_identical_and_device_is_statistical(tt, golden):
+    pt = tt.particle_tracker
+    g = golden("init_beam")
+    x = np.linspace(-5e-3, 5e-3, 9)
+    for d in "xyz":
+        cube = pt.ElectronCube(x, x * 0.8, x * 1.2, probing_direction=d)
+        np.random.seed(5)
+        cube.init_beam(257, 2e-3, 5e-3)
+        np.testing.assert_array_equal(cube.s0, g["s0_" + d])
+        assert cube.extent == float(g["extent_" + d])
+    cube = pt.ElectronCube(x, x, x)
+    cube.init_beam(400000, 2e-3, 5e-3, seed=42)
+    s = np.asarray(cube.s0)
+    r = np.hypot(s[0], s[1])
+    assert r.max() <= 2e-3 and np.all(s[2] == -5e-3)
+    assert np.mean(r) == pytest.approx(2e-3 * 2 / 3, rel=5e-3)           # folded sum of two uniforms: pdf 2u
+    chi = np.arccos(np.clip(s[5] / orc.C_LIGHT, -1, 1))
+    assert np.sqrt(np.mean(chi**2)) == pytest.approx(5e-3, rel=1e-2)
+    np.testing.assert_allclose(np.sqrt(s[3] ** 2 + s[4] ** 2 + s[5] ** 2), orc.C_LIGHT, rtol=1e-14)
+    # shards are addressable: rays [1000, 2000) of the same seed
+    cube.init_beam(1000, 2e-3, 5e-3, seed=42, first_ray=1000)
+    np.testing.assert_array_equal(np.asarray(cube.s0), s[:, 1000:2000])
+
+
+# ------------------------------------------------------------------------------------------- K5/K6
+def test_optics_elements_match_reference(tt, golden):
+    rtm = tt.ray_transfer_matrix
+    g = golden("optics")
+    r = g["m_to_mm"]
+    close = lambda a, k: np.testing.assert_allclose(np.asarray(a), g[k], rtol=1e-14, atol=0, equal_nan=True)
+    np.testing.assert_array_equal(rtm.m_to_mm(g["r0"]), r)
+    close(rtm.lens(r.copy(), 300.0, 150.0), "lens")
+    close(rtm.sym_lens(r.copy(), 250.0), "sym_lens")
+    close(rtm.distance(r.copy(), 123.0), "distance")
+    for fn, args, key in [(rtm.circular_aperture, (3.0,), "circular_aperture"), (rtm.circular_stop, (3.0,), "circular_stop"),
+                          (rtm.angular_filter, (np.arange(0, 6, 0.5),), "angular_filter"),
+                          (rtm.rect_aperture, (2.0, 1.0), "rect_aperture"),
+                          (rtm.knife_edge, (0.5, "y", 1), "knife_edge_y_pos"), (rtm.knife_edge, (-0.5, "x", -1), "knife_edge_x_neg")]:
+        a = r.copy()
+        out = fn(a, *args)
+        assert out is a                                   # in place, like the reference
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(g[key]))
+        close(a, key)
+    np.testing.assert_array_equal(rtm.annular_stop(r.copy(), 1.0, 2.5), g["annular_stop"])
+
+
+def test_detectors_and_histograms_match_reference(tt, golden):
+    rtm = tt.ray_transfer_matrix
+    g = golden("optics")
+    r0 = g["r0"]
+    dets = {
+        "sh": (rtm.Shadowgraphy, dict(), dict(L=400, R=25, Lx=18, Ly=13.5, focal_plane=0)),
+        "sh_fp": (rtm.Shadowgraphy, dict(), dict(L=400, R=25, Lx=6, Ly=6, focal_plane=5)),
+        "df": (rtm.Schlieren_DF, dict(R=3), dict(L=400, R=25, Lx=6, Ly=6)),
+        "lf": (rtm.Schlieren_LF, dict(R=3), dict(L=400, R=25, Lx=6, Ly=6)),
+        "afr": (rtm.AFR, dict(Rs=np.arange(0, 6, 0.5)), dict(focal_plane=5, L=100, R=25, Lx=15, Ly=10)),
+    }
+    H = {}
+    for k, (cls, skw, ckw) in dets.items():
+        # fused path: histogram straight from r0 (rf never materialised)
+        d = cls(r0, **ckw)
+        d.solve(**skw)
+        d.histogram(bin_scale=25)
+        np.testing.assert_array_equal(d.H, g[k + "_H"])
+        np.testing.assert_array_equal(d.xedges, g[k + "_xedges"])
+        np.testing.assert_array_equal(d.yedges, g[k + "_yedges"])
+        assert d.H.dtype == np.float64 and d.H.shape == (2574 // 25, 3448 // 25)
+        np.testing.assert_allclose(np.asarray(d.rf), g[k + "_rf"], rtol=1e-13, atol=1e-13, equal_nan=True)
+        # two-pass path: rf first, then binning of rf
+        d2 = cls(r0, **ckw)
+        d2.solve(**skw)
+        _ = d2.rf
+        d2.histogram(bin_scale=25, clear_mem=True)
+        np.testing.assert_array_equal(d2.H, g[k + "_H"])
+        assert d2.rf is None and d2.r0 is None
+        H[k] = d.H
+    d = rtm.Shadowgraphy(r0)
+    d.solve()
+    d.histogram()
+    np.testing.assert_array_equal(d.H, g["sh_default_H"])
+    assert d.H.shape == (257, 344)
+    sh6 = rtm.Shadowgraphy(r0, L=400, R=25, Lx=6, Ly=6)
+    sh6.solve()
+    sh6.histogram(bin_scale=25)
+    np.testing.assert_array_equal(H["df"] + H["lf"], sh6.H)      # notebook cells 16-19
+
+
+def test_histogram_edge_semantics(tt):
+    """numpy.histogram2d conventions: right-open bins, last edge inclusive, outside and NaN dropped."""
+    rtm = tt.ray_transfer_matrix
+    xe = np.linspace(-9, 9, 345)
+    vals = np.array([-9.0, 9.0, xe[17], np.nextafter(xe[17], -np.inf), 9.0000001, -9.0000001, np.nan, 0.0]) * 1e-3
+    r = np.zeros((4, vals.size))
+    r[0] = vals
+    r[2] = 0.0
+    d = rtm.Rays(r)
+    d.rf = rtm.m_to_mm(r)
+    d.histogram()
+    Href, _, _ = orc.histogram(orc.m_to_mm(r))
+    np.testing.assert_array_equal(d.H, Href)
+    assert 3 <= d.H.sum() <= 5
+
+
+# ------------------------------------------------------------------------------------------- K7
+def test_grf_matches_reference(tt, golden):
+    tg = tt.turboGen
+    g = golden("grf")
+    N = int(g["N3"])
+    np.random.seed(33)
+    f = tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0))
+    assert f.shape == (2 * N + 1,) * 3 and f.dtype == np.float64
+    np.testing.assert_allclose(f, g["f3"], rtol=0, atol=1e-12 * np.abs(g["f3"]).max())
+    np.random.seed(33)
+    f32 = tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), dtype="float32")
+    np.testing.assert_allclose(f32, g["f3"], rtol=0, atol=2e-6 * np.abs(g["f3"]).max())
+
+
+def test_grf_device_rng_statistics(tt):
+    """Philox path: zero mean, reproducible per seed, and the power spectrum follows k_func."""
+    tg = tt.turboGen
+    N = 32
+    M = 2 * N + 1
+    f = tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=3)
+    assert abs(f.mean()) < 1e-12 * np.abs(f).max() * M**3
+    np.testing.assert_array_equal(f, tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=3))
+    assert not np.array_equal(f, tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=4))
+    F = np.fft.fftn(f)
+    k = np.fft.fftfreq(M)
+    K = np.sqrt(k[:, None, None] ** 2 + k[None, :, None] ** 2 + k[None, None, :] ** 2)
+    P = np.abs(F) ** 2
+    sel = (K > 0.05) & (K < 0.45)
+    slope = np.polyfit(np.log(K[sel]), np.log(P[sel]), 1)[0]
+    assert slope == pytest.approx(-11.0 / 3.0, abs=0.1)
+    # white spectrum: variance of the field = sum |F|^2 / M^6 with E|W|^2 = 4 per mode
+    w = tg.gaussian3D_FFT(N, lambda k: np.ones_like(k), seed=5)
+    assert w.var() == pytest.approx(4.0 * (M**3 - 1) / M**6, rel=0.02)
+
+
+# ------------------------------------------------------------------------------------------- scale
+def test_large_bundle_properties(tt):
+    """1e6 rays through a 129^3 random cube: properties that do not need the CPU oracle."""
+    import torch
+    pt, rtm, tg = tt.particle_tracker, tt.ray_transfer_matrix, tt.turboGen
+    f = tg.gaussian3D_FFT(64, lambda k: k ** (-11.0 / 3.0), seed=11, dtype="float32", return_device=True).torch
+    ne = 1e25 * torch.clamp(1 + 0.3 * f / f.std(), min=0)
+    x = np.linspace(-5e-3, 5e-3, 129)
+    res = {}
+    for dtype in ("float32", "float64"):
+        cube = pt.ElectronCube(x, x, x, dtype=dtype, verbose=False, keep_sf=False)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        cube.init_beam(1_000_000, 4e-3, 0.05e-3, seed=1)
+        rf = cube.solve(return_status=True)
+        assert cube.ray_steps == 128 * 1_000_000
+        assert int((cube.status.torch == 1).sum()) == 1_000_000
+        res[dtype] = rf
+    a, b = res["float32"].torch, res["float64"].torch
+    dpos = max(float((a[0] - b[0]).abs().max()), float((a[2] - b[2]).abs().max()))
+    print(f"129^3, 1e6 rays: fp32 vs fp64 max position difference {dpos:.3e} m = {dpos / PIXEL_M:.2e} pixel")
+    assert dpos <= 1e-3 * PIXEL_M
+    sh = rtm.Shadowgraphy(res["float32"], L=400, R=25, Lx=18, Ly=13.5); sh.solve(); sh.histogram()
+    df = rtm.Schlieren_DF(res["float32"]); df.solve(R=1); df.histogram()
+    lf = rtm.Schlieren_LF(res["float32"]); lf.solve(R=1); lf.histogram()
+    assert sh.H.sum() == 1_000_000
+    np.testing.assert_array_equal(df.H + lf.H, sh.H)
+    # device histogram == numpy.histogram2d on the same detector-plane rays
+    Href, _, _ = orc.histogram(np.asarray(sh.rf))
+    np.testing.assert_array_equal(sh.H, Href)

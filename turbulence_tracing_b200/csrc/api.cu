@@ -1,0 +1,104 @@
+// Error state, version and the host-buffer convenience entry point of libtt_b200.so.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace tt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return TT_ERR_CUDA;
+}
+
+}  // namespace tt
+
+extern "C" int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
+
+extern "C" const char* tt_last_error(void) { return tt::g_err; }
+
+extern "C" int tt_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        tt::cuda_fail(e, "cudaGetDeviceCount");
+        return -1;
+    }
+    return n;
+}
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+}  // namespace
+
+// Whole path for one bundle with host arrays (ElectronCube.external_ne + calc_dndr + solve):
+// the call a ctypes binding inside the reference would make.
+extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const double origin_xyz[3],
+                             const double spacing_xyz[3], int par, double nc, double ne_max, double extent,
+                             int steps_per_cell, int dtype, const double* s0_host, long np, double* rf_host,
+                             double* sf_host, unsigned long long* ray_steps_host) {
+    using namespace tt;
+    TT_REQUIRE(ne_host && n_xyz && origin_xyz && spacing_xyz && s0_host && rf_host, "tt_solve_host: null pointer");
+    TT_REQUIRE(np >= 0 && np < (1L << 31), "tt_solve_host: ray count must be in [0, 2^31)");
+    TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_solve_host: dtype must be TT_F32 or TT_F64");
+    for (int i = 0; i < 3; ++i) TT_REQUIRE(n_xyz[i] >= 2, "tt_solve_host: every axis needs >= 2 points");
+    if (tt_device_count() <= 0) {
+        set_error("tt_solve_host: no CUDA device (there is no CPU fallback)");
+        return TT_ERR_CUDA;
+    }
+    const size_t nvox = (size_t)n_xyz[0] * n_xyz[1] * n_xyz[2];
+    size_t sort_bytes = 0;
+    int rc = tt_sort_rays_workspace(np, &sort_bytes);
+    if (rc) return rc;
+    DevBuf ne, grid, s0, rf, sf, perm, ws, cnt;
+    TT_CUDA(ne.alloc(nvox * sizeof(double)));
+    TT_CUDA(grid.alloc(nvox * (dtype == TT_F32 ? 16 : 32)));
+    TT_CUDA(s0.alloc((size_t)np * 6 * sizeof(double)));
+    TT_CUDA(rf.alloc((size_t)np * 4 * sizeof(double)));
+    if (sf_host) TT_CUDA(sf.alloc((size_t)np * 6 * sizeof(double)));
+    TT_CUDA(perm.alloc((size_t)np * sizeof(uint32_t)));
+    TT_CUDA(ws.alloc(sort_bytes));
+    TT_CUDA(cnt.alloc(sizeof(unsigned long long)));
+    cudaStream_t s = 0;
+    TT_CUDA(cudaMemcpyAsync(ne.p, ne_host, nvox * sizeof(double), cudaMemcpyHostToDevice, s));
+    TT_CUDA(cudaMemcpyAsync(s0.p, s0_host, (size_t)np * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+    TT_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
+    rc = tt_calc_dndr(ne.p, TT_F64, n_xyz, spacing_xyz, par, nc, ne_max, grid.p, dtype, s);
+    if (rc) return rc;
+    rc = tt_sort_rays((const double*)s0.p, np, par, origin_xyz, spacing_xyz, n_xyz, (uint32_t*)perm.p, ws.p,
+                      sort_bytes, s);
+    if (rc) return rc;
+    tt_trace_params p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 3; ++i) {
+        p.n_xyz[i] = n_xyz[i];
+        p.origin_xyz[i] = origin_xyz[i];
+        p.spacing_xyz[i] = spacing_xyz[i];
+    }
+    p.par = par;
+    p.extent = extent;
+    p.s_max = 2.8284271247461903 * extent;   // sqrt(8) * extent (particle_tracker.py:317)
+    p.steps_per_cell = steps_per_cell;
+    p.dtype = dtype;
+    rc = tt_trace(&p, grid.p, (const double*)s0.p, np, (const uint32_t*)perm.p, (double*)rf.p, (double*)sf.p,
+                  (unsigned long long*)cnt.p, nullptr, s);
+    if (rc) return rc;
+    TT_CUDA(cudaMemcpyAsync(rf_host, rf.p, (size_t)np * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sf_host) TT_CUDA(cudaMemcpyAsync(sf_host, sf.p, (size_t)np * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ray_steps_host)
+        TT_CUDA(cudaMemcpyAsync(ray_steps_host, cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    TT_CUDA(cudaStreamSynchronize(s));
+    return TT_OK;
+}

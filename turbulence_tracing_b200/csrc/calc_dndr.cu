@@ -1,0 +1,139 @@
+// K1: gradient-grid stencil.  Replaces ElectronCube.calc_dndr (particle_tracker.py:220-241):
+// three numpy.gradient passes + three RegularGridInterpolator objects become ONE pass that
+// writes an interleaved 4-vector grid (g_u, g_v, g_w, ne/nc) in ray-frame order, so that a
+// trilinear corner is a single 16-byte (FP32) or 32-byte (FP64) load in the trace kernel.
+//
+// Memory behaviour: input ne[ix][iy][iz] is z-fastest; output grid[iw][iv][iu] is u-fastest
+// and u is never z, so every block transposes a 32(z) x 32(u) tile through shared memory:
+// reads are coalesced along z, writes along u.  Algorithmic traffic: read sizeof(ne) per voxel
+// (neighbour reads hit L1/L2), write 16 or 32 B per voxel.
+#include "common.cuh"
+
+namespace tt {
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<double> { typedef double4 type; };
+
+struct DndrArgs {
+    int n[3];          // nx, ny, nz
+    double inv2h[3];   // unused placeholder kept for alignment
+    double h[3];       // spacing per axis (x, y, z)
+    int fa[3];         // frame: (u, v, w) -> xyz axis
+    double nc, ne_max;
+    int third;         // the xyz axis that is neither z nor the u axis
+};
+
+template <typename TIn>
+__device__ __forceinline__ double ne_over_nc(const TIn* __restrict__ ne, size_t idx, double nc,
+                                             double ne_max) {
+    double v = (double)ne[idx] / nc;     // particle_tracker.py:230
+    return v > ne_max ? ne_max : v;      // :231 (NaN stays NaN, as with numpy's mask)
+}
+
+// numpy.gradient along one axis at index i of n: central inside, one-sided at the two faces
+// (edge_order=1, numpy/lib/_function_base_impl.py:1294-1334), uniform spacing h.
+template <typename TIn>
+__device__ __forceinline__ double axis_gradient(const TIn* __restrict__ ne, size_t idx, size_t stride,
+                                                int i, int n, double h, double centre, double nc,
+                                                double ne_max) {
+    if (n == 1) return 0.0;
+    if (i == 0) return (ne_over_nc(ne, idx + stride, nc, ne_max) - centre) / h;
+    if (i == n - 1) return (centre - ne_over_nc(ne, idx - stride, nc, ne_max)) / h;
+    return (ne_over_nc(ne, idx + stride, nc, ne_max) - ne_over_nc(ne, idx - stride, nc, ne_max)) /
+           (2.0 * h);
+}
+
+template <typename TIn, typename TOut, int PAR>
+__global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ ne,
+                                                        typename Vec4<TOut>::type* __restrict__ grid,
+                                                        DndrArgs a) {
+    typedef typename Vec4<TOut>::type V4;
+    __shared__ V4 tile[32][33];
+    // frame (u, v, w) -> xyz axis, compile-time so that the index arrays stay in registers
+    constexpr int F0 = PAR == 0 ? 1 : 0, F1 = PAR == 2 ? 1 : 2, F2 = PAR;
+    constexpr int ua = F0;                  // xyz axis that is fastest in the output
+    constexpr int ta = 1 - F0;              // the axis that is neither z nor u
+    const int z0 = blockIdx.x * 32, u0 = blockIdx.y * 32, t = blockIdx.z;
+    const int nx = a.n[0], ny = a.n[1], nz = a.n[2];
+    const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
+
+    // phase 1: compute, coalesced along z
+    const int iz = z0 + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int iu = u0 + r + threadIdx.y;
+        if (iz < nz && iu < a.n[ua]) {
+            int i3[3];
+            i3[2] = iz; i3[ua] = iu; i3[ta] = t;
+            const size_t idx = (size_t)i3[0] * sx + (size_t)i3[1] * sy + i3[2];
+            const double c = ne_over_nc(ne, idx, a.nc, a.ne_max);
+            double g[3];
+            g[0] = -0.5 * axis_gradient(ne, idx, sx, i3[0], nx, a.h[0], c, a.nc, a.ne_max);
+            g[1] = -0.5 * axis_gradient(ne, idx, sy, i3[1], ny, a.h[1], c, a.nc, a.ne_max);
+            g[2] = -0.5 * axis_gradient(ne, idx, 1, i3[2], nz, a.h[2], c, a.nc, a.ne_max);
+            V4 o;
+            o.x = (TOut)g[F0]; o.y = (TOut)g[F1]; o.z = (TOut)g[F2]; o.w = (TOut)c;
+            tile[r + threadIdx.y][threadIdx.x] = o;
+        }
+    }
+    __syncthreads();
+    // phase 2: write, coalesced along u
+    const int ou = u0 + threadIdx.x;
+    const int nu = a.n[F0], nv = a.n[F1];
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int oz = z0 + r + threadIdx.y;
+        if (ou < nu && oz < nz) {
+            int i3[3];
+            i3[2] = oz; i3[ua] = ou; i3[ta] = t;
+            const int iv = i3[F1], iw = i3[F2];
+            grid[((size_t)iw * nv + iv) * nu + ou] = tile[threadIdx.x][r + threadIdx.y];
+        }
+    }
+}
+
+template <typename TIn, typename TOut>
+static int launch_dndr(const void* ne, void* grid, const DndrArgs& a, cudaStream_t s) {
+    dim3 block(32, 8);
+    dim3 gridDim((a.n[2] + 31) / 32, (a.n[a.fa[0]] + 31) / 32, a.n[a.third]);
+    typedef typename Vec4<TOut>::type V4;
+    const int par = a.fa[2];
+    if (par == 0) calc_dndr_kernel<TIn, TOut, 0><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
+    else if (par == 1) calc_dndr_kernel<TIn, TOut, 1><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
+    else calc_dndr_kernel<TIn, TOut, 2><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
+    return launch_check("calc_dndr_kernel");
+}
+
+}  // namespace tt
+
+extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3],
+                            const double spacing_xyz[3], int par, double nc, double ne_max,
+                            void* grid4_dev, int grid_dtype, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(ne_dev && grid4_dev && n_xyz && spacing_xyz, "tt_calc_dndr: null pointer");
+    TT_REQUIRE(par >= 0 && par <= 2, "tt_calc_dndr: par must be 0, 1 or 2 (got %d)", par);
+    TT_REQUIRE((ne_dtype == TT_F32 || ne_dtype == TT_F64) && (grid_dtype == TT_F32 || grid_dtype == TT_F64),
+               "tt_calc_dndr: dtype must be TT_F32 or TT_F64");
+    DndrArgs a;
+    for (int i = 0; i < 3; ++i) {
+        TT_REQUIRE(n_xyz[i] >= 2, "tt_calc_dndr: every axis needs >= 2 points (axis %d has %d)", i, n_xyz[i]);
+        TT_REQUIRE(spacing_xyz[i] > 0, "tt_calc_dndr: spacing must be > 0");
+        a.n[i] = n_xyz[i];
+        a.h[i] = spacing_xyz[i];
+        a.inv2h[i] = 0;
+    }
+    TT_REQUIRE(n_xyz[0] <= 65535 * 32 && n_xyz[1] <= 65535 * 32, "tt_calc_dndr: cube too large");
+    TT_REQUIRE(nc > 0, "tt_calc_dndr: critical density must be > 0");
+    Frame f = frame_of(par);
+    for (int i = 0; i < 3; ++i) a.fa[i] = f.a[i];
+    a.third = 3 - 2 - a.fa[0];   // axes are {0,1,2}; z = 2 and u = fa[0] are taken
+    a.nc = nc;
+    a.ne_max = ne_max;
+    TT_REQUIRE(a.n[a.third] <= 65535, "tt_calc_dndr: axis too long for grid.z");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ne_dtype == TT_F32 && grid_dtype == TT_F32) return launch_dndr<float, float>(ne_dev, grid4_dev, a, s);
+    if (ne_dtype == TT_F64 && grid_dtype == TT_F32) return launch_dndr<double, float>(ne_dev, grid4_dev, a, s);
+    if (ne_dtype == TT_F32 && grid_dtype == TT_F64) return launch_dndr<float, double>(ne_dev, grid4_dev, a, s);
+    return launch_dndr<double, double>(ne_dev, grid4_dev, a, s);
+}

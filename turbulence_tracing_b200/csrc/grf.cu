@@ -1,0 +1,137 @@
+// K7: Gaussian-random-field synthesis.  Replaces turboGen.gaussian3D_FFT
+// (gaussian_fields/turboGen.py:488-538): instead of building K, Wr, Wi, flip(Wr), flip(Wi), W, F
+// and ifftshift(F) as eight M^3 temporaries and running a complex ifftn, one kernel writes the
+// HALF spectrum F[a][b][0..N] directly in FFT (unshifted) order -- the field is Hermitian by
+// construction (W = Wr + flip(Wr) + i (Wi - flip(Wi)), :525-528) -- and cuFFT runs one
+// complex-to-real inverse transform.  sqrt(P(|k|)) comes from a table indexed by the integer
+// q = fa^2 + fb^2 + fc^2 (|k| = sqrt(q)/M), evaluated once on the host from the user's k_func.
+#include "common.cuh"
+
+#include <cufft.h>
+
+namespace tt {
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float> { typedef float2 type; };
+template <> struct Cplx<double> { typedef double2 type; };
+
+__device__ __forceinline__ void philox_normals(uint64_t idx, uint64_t seed, double& wr, double& wi) {
+    const double two_pi = 6.283185307179586476925;
+    Philox p = philox4x32_10(idx, 0x47524621ull /* 'GRF!' */, seed);
+    Philox q = philox4x32_10(idx, 0x47524622ull, seed);
+    wr = sqrt(-2.0 * log(u01(p.c[0], p.c[1]))) * cos(two_pi * u01(p.c[2], p.c[3]));
+    wi = sqrt(-2.0 * log(u01(q.c[0], q.c[1]))) * cos(two_pi * u01(q.c[2], q.c[3]));
+}
+
+// one thread per element of the half spectrum (a, b, c), c = 0..N
+template <typename T>
+__global__ void __launch_bounds__(256) grf_spectrum_kernel(int N, const double* __restrict__ lut,
+                                                           const double* __restrict__ Wr,
+                                                           const double* __restrict__ Wi, uint64_t seed,
+                                                           double norm, typename Cplx<T>::type* __restrict__ F) {
+    const int M = 2 * N + 1, Nh = N + 1;
+    const size_t total = (size_t)M * M * Nh;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % Nh);
+    const int b = (int)((i / Nh) % M);
+    const int a = (int)(i / ((size_t)Nh * M));
+    // signed frequencies of FFT-order indices
+    const int fa = a <= N ? a : a - M, fb = b <= N ? b : b - M, fc = c;
+    // index of +k and of -k in the fftshift-ed cubes Wr, Wi (:520-526)
+    const size_t jp = ((size_t)(N + fa) * M + (N + fb)) * M + (N + fc);
+    const size_t jm = ((size_t)(N - fa) * M + (N - fb)) * M + (N - fc);
+    double wrp, wip, wrm, wim;
+    if (Wr) {
+        wrp = Wr[jp]; wrm = Wr[jm]; wip = Wi[jp]; wim = Wi[jm];
+    } else {
+        philox_normals(jp, seed, wrp, wip);
+        philox_normals(jm, seed, wrm, wim);
+    }
+    const int q = fa * fa + fb * fb + fc * fc;
+    // F[0,0,0] = 0 (:534); numpy's ifftn normalisation 1/M^3 (:536) is folded into the amplitude
+    const double amp = q == 0 ? 0.0 : lut[q] * norm;
+    typename Cplx<T>::type o;
+    o.x = (T)((wrp + wrm) * amp);
+    o.y = (T)((wip - wim) * amp);
+    if (q == 0) { o.x = T(0); o.y = T(0); }
+    F[i] = o;
+}
+
+static int cufft_fail(cufftResult r, const char* what) {
+    set_error("cuFFT error %d in %s", (int)r, what);
+    return TT_ERR_CUDA;
+}
+#define TT_FFT(call)                                              \
+    do {                                                          \
+        cufftResult r_ = (call);                                  \
+        if (r_ != CUFFT_SUCCESS) return cufft_fail(r_, #call);    \
+    } while (0)
+
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static int plan_size(int N, int dtype, size_t* spectrum_bytes, size_t* work_bytes) {
+    const int M = 2 * N + 1;
+    *spectrum_bytes = align256((size_t)M * M * (N + 1) * (dtype == TT_F32 ? 8 : 16));
+    cufftHandle plan;
+    TT_FFT(cufftCreate(&plan));
+    cufftResult r = cufftSetAutoAllocation(plan, 0);
+    if (r == CUFFT_SUCCESS) r = cufftMakePlan3d(plan, M, M, M, dtype == TT_F32 ? CUFFT_C2R : CUFFT_Z2D, work_bytes);
+    cufftDestroy(plan);
+    if (r != CUFFT_SUCCESS) return cufft_fail(r, "cufftMakePlan3d(size query)");
+    return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" int tt_grf_workspace(int N, int dtype, size_t* bytes) {
+    using namespace tt;
+    TT_REQUIRE(bytes, "tt_grf_workspace: null pointer");
+    TT_REQUIRE(N >= 1 && N <= 2047, "tt_grf: N out of range");
+    TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_grf: dtype must be TT_F32 or TT_F64");
+    size_t spec = 0, work = 0;
+    int rc = plan_size(N, dtype, &spec, &work);
+    if (rc) return rc;
+    *bytes = spec + align256(work);
+    return TT_OK;
+}
+
+extern "C" int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev, const double* Wi_dev,
+                        uint64_t seed, void* out_dev, void* workspace_dev, size_t workspace_bytes,
+                        tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(sqrtP_lut_dev && out_dev && workspace_dev, "tt_grf3d: null pointer");
+    TT_REQUIRE((Wr_dev == nullptr) == (Wi_dev == nullptr), "tt_grf3d: give both Wr and Wi or neither");
+    TT_REQUIRE(N >= 1 && N <= 2047, "tt_grf3d: N out of range");
+    TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_grf3d: dtype must be TT_F32 or TT_F64");
+    size_t spec = 0, work = 0;
+    int rc = plan_size(N, dtype, &spec, &work);
+    if (rc) return rc;
+    TT_REQUIRE(workspace_bytes >= spec + align256(work), "tt_grf3d: workspace too small");
+    const int M = 2 * N + 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t total = (size_t)M * M * (N + 1);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const double norm = 1.0 / ((double)M * M * M);
+    if (dtype == TT_F32)
+        grf_spectrum_kernel<float><<<blocks, 256, 0, s>>>(N, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (float2*)workspace_dev);
+    else
+        grf_spectrum_kernel<double><<<blocks, 256, 0, s>>>(N, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (double2*)workspace_dev);
+    rc = launch_check("grf_spectrum_kernel");
+    if (rc) return rc;
+
+    cufftHandle plan;
+    TT_FFT(cufftCreate(&plan));
+    size_t ws = 0;
+    cufftResult r = cufftSetAutoAllocation(plan, 0);
+    if (r == CUFFT_SUCCESS) r = cufftMakePlan3d(plan, M, M, M, dtype == TT_F32 ? CUFFT_C2R : CUFFT_Z2D, &ws);
+    if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(plan, (char*)workspace_dev + spec);
+    if (r == CUFFT_SUCCESS) r = cufftSetStream(plan, s);
+    if (r == CUFFT_SUCCESS) {
+        if (dtype == TT_F32) r = cufftExecC2R(plan, (cufftComplex*)workspace_dev, (cufftReal*)out_dev);
+        else r = cufftExecZ2D(plan, (cufftDoubleComplex*)workspace_dev, (cufftDoubleReal*)out_dev);
+    }
+    cufftDestroy(plan);
+    if (r != CUFFT_SUCCESS) return cufft_fail(r, "cuFFT C2R plan/exec");
+    return TT_OK;
+}

@@ -1,0 +1,498 @@
+// K3 + K4: the ray integrator.  Replaces ElectronCube.solve / dsdt / dndr / ray_at_exit
+// (particle_tracker.py:312-331, 398-419, 243-256, 333-380), i.e. scipy's global-step RK45 over
+// three RegularGridInterpolator objects, by ONE kernel: one thread per ray, fixed-step RK4.
+//
+// Formulation (not a translation of the reference):
+//   * non-dimensional state: position in grid-index units held as (int cell, fraction) per
+//     axis, direction d = v/c, path time s = c*t.  Equations of motion
+//         dX/ds = d / h,   dd/ds = g(X),   g = -1/2 grad(ne/nc)   (the reference's dnd?/c^2).
+//   * plane marching: the probing-axis coordinate W is the independent variable,
+//         dU/dW = (hw/hu) du/dw,  d(d)/dW = hw g/dw,  ds/dW = hw/dw,
+//     so every RK4 step starts and ends exactly on a grid (sub-)plane of the probing axis and
+//     never straddles the kink of the piecewise-trilinear field at a cell face in W.
+//     steps_per_cell sub-planes per cell.  Stage coordinates are clamped into the cube; a ray
+//     that would leave through a side face is re-stepped to the face and frozen there.
+//   * rays that are steep or move backwards (d_w <= kMarchMinDw), and rays about to hit the
+//     path-time cap s_max = c*T, continue in a general arc-length RK4 with the same field.
+//   * outside the cube the field is exactly zero (fill_value=0.0), so rays are straight lines:
+//     the prologue moves a ray launched outside to its entry point, the epilogue projects the
+//     frozen exit state to the plane par-axis = +extent (ray_at_exit) and, if asked, to time T
+//     (the reference's cube.sf).
+// Template parameter T is the arithmetic/grid type: float (16 B corners) or double (32 B).
+#include "common.cuh"
+
+namespace tt {
+
+static constexpr double kC = 299792458.0;      // scipy.constants.c (particle_tracker.py:119)
+#define TT_MARCH_MIN_DW 0.75
+
+struct TraceArgs {
+    int n[3];        // nu, nv, nw
+    double o[3];     // origin per frame axis
+    double h[3];     // spacing per frame axis
+    int fa[3];       // frame axis -> xyz row
+    double extent, s_max;
+    int spc;
+    long np;
+};
+
+template <typename T> struct GridT;
+template <> struct GridT<float> {
+    typedef float4 V4;
+    static __device__ __forceinline__ float4 ld(const float4* p) { return __ldg(p); }
+};
+template <> struct GridT<double> {
+    typedef double4 V4;
+    static __device__ __forceinline__ double4 ld(const double4* p) {
+        const double2* q = reinterpret_cast<const double2*>(p);
+        double2 a = __ldg(q), b = __ldg(q + 1);
+        return make_double4(a.x, a.y, b.x, b.y);
+    }
+};
+
+template <typename T> __device__ __forceinline__ T tfloor(T x);
+template <> __device__ __forceinline__ float tfloor<float>(float x) { return floorf(x); }
+template <> __device__ __forceinline__ double tfloor<double>(double x) { return floor(x); }
+template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
+template <> __device__ __forceinline__ float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// cell/fraction of coordinate (i + f) clamped into [0, n-1]; the upper face is cell n-2, t = 1
+// (as scipy's find_indices does for x == grid[-1]).
+template <typename T>
+__device__ __forceinline__ void cell_of(int i, T f, int n, int& c, T& t) {
+    T fl = tfloor(f);
+    c = i + (int)fl;
+    t = f - fl;
+    if (c < 0) { c = 0; t = T(0); }
+    if (c > n - 2) { c = n - 2; t = T(1); }
+}
+
+template <typename T> struct G3 { T x, y, z; };
+
+// trilinear gradient in cell (cu, cv, cw) at fractions (tu, tv, tw)
+template <typename T>
+__device__ __forceinline__ G3<T> trilinear(const typename GridT<T>::V4* __restrict__ grid, int nu,
+                                           size_t plane, int cu, int cv, int cw, T tu, T tv, T tw) {
+    typedef typename GridT<T>::V4 V4;
+    const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
+    V4 c000 = GridT<T>::ld(p), c100 = GridT<T>::ld(p + 1);
+    V4 c010 = GridT<T>::ld(p + nu), c110 = GridT<T>::ld(p + nu + 1);
+    p += plane;
+    V4 c001 = GridT<T>::ld(p), c101 = GridT<T>::ld(p + 1);
+    V4 c011 = GridT<T>::ld(p + nu), c111 = GridT<T>::ld(p + nu + 1);
+    G3<T> g;
+#define TT_TRI(m)                                                        \
+    {                                                                    \
+        T a00 = tfma(tu, c100.m - c000.m, c000.m);                       \
+        T a10 = tfma(tu, c110.m - c010.m, c010.m);                       \
+        T a01 = tfma(tu, c101.m - c001.m, c001.m);                       \
+        T a11 = tfma(tu, c111.m - c011.m, c011.m);                       \
+        T b0 = tfma(tv, a10 - a00, a00);                                 \
+        T b1 = tfma(tv, a11 - a01, a01);                                 \
+        g.m = tfma(tw, b1 - b0, b0);                                     \
+    }
+    TT_TRI(x) TT_TRI(y) TT_TRI(z)
+#undef TT_TRI
+    return g;
+}
+
+template <typename T>
+struct Ray {
+    int iu, iv, iw;
+    T fu, fv, fw;     // fractions relative to (iu, iv, iw); may be un-normalised after a step
+    T du, dv, dw;
+    T s;              // path time c*t accumulated inside the cube
+};
+
+template <typename T>
+struct Consts {
+    int nu, nv, nw;
+    size_t plane;
+    T ru, rv, hw;     // hw/hu, hw/hv, hw  (plane marching)
+    T iu_, iv_, iw_;  // 1/hu, 1/hv, 1/hw  (arc-length stepping)
+};
+
+// One RK4 step in W from fraction fwa to fwa + h inside w-cell k (0 <= fwa, fwa + h <= 1).
+// Updates fu, fv (un-normalised), d and s of r.  Returns false if a stage saw d_w <= 0.
+template <typename T>
+__device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+                                      Ray<T>& r, int k, T fwa, T h) {
+    const T half = T(0.5) * h;
+    int cu, cv; T tu, tv;
+    // stage 1
+    cell_of(r.iu, r.fu, C.nu, cu, tu); cell_of(r.iv, r.fv, C.nv, cv, tv);
+    G3<T> g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa);
+    T inv = C.hw / r.dw;
+    T aU = C.ru * r.du / r.dw, aV = C.rv * r.dv / r.dw;
+    T adu = g.x * inv, adv = g.y * inv, adw = g.z * inv, as = inv;
+    bool ok = r.dw > T(0);
+    // stage 2
+    T du = tfma(half, adu, r.du), dv = tfma(half, adv, r.dv), dw = tfma(half, adw, r.dw);
+    cell_of(r.iu, tfma(half, aU, r.fu), C.nu, cu, tu); cell_of(r.iv, tfma(half, aV, r.fv), C.nv, cv, tv);
+    g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa + half);
+    ok = ok && dw > T(0);
+    inv = C.hw / dw;
+    T bU = C.ru * du / dw, bV = C.rv * dv / dw;
+    T bdu = g.x * inv, bdv = g.y * inv, bdw = g.z * inv, bs = inv;
+    // stage 3
+    du = tfma(half, bdu, r.du); dv = tfma(half, bdv, r.dv); dw = tfma(half, bdw, r.dw);
+    cell_of(r.iu, tfma(half, bU, r.fu), C.nu, cu, tu); cell_of(r.iv, tfma(half, bV, r.fv), C.nv, cv, tv);
+    g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa + half);
+    ok = ok && dw > T(0);
+    inv = C.hw / dw;
+    T cU = C.ru * du / dw, cV = C.rv * dv / dw;
+    T cdu = g.x * inv, cdv = g.y * inv, cdw = g.z * inv, cs = inv;
+    // stage 4
+    du = tfma(h, cdu, r.du); dv = tfma(h, cdv, r.dv); dw = tfma(h, cdw, r.dw);
+    cell_of(r.iu, tfma(h, cU, r.fu), C.nu, cu, tu); cell_of(r.iv, tfma(h, cV, r.fv), C.nv, cv, tv);
+    T fwb = fwa + h;
+    g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwb > T(1) ? T(1) : fwb);
+    ok = ok && dw > T(0);
+    inv = C.hw / dw;
+    T eU = C.ru * du / dw, eV = C.rv * dv / dw;
+    T edu = g.x * inv, edv = g.y * inv, edw = g.z * inv, es = inv;
+    const T h6 = h * T(1.0 / 6.0);
+    r.fu = tfma(h6, aU + T(2) * (bU + cU) + eU, r.fu);
+    r.fv = tfma(h6, aV + T(2) * (bV + cV) + eV, r.fv);
+    r.du = tfma(h6, adu + T(2) * (bdu + cdu) + edu, r.du);
+    r.dv = tfma(h6, adv + T(2) * (bdv + cdv) + edv, r.dv);
+    r.dw = tfma(h6, adw + T(2) * (bdw + cdw) + edw, r.dw);
+    r.s = tfma(h6, as + T(2) * (bs + cs) + es, r.s);
+    return ok;
+}
+
+// One RK4 step of length ds in path time (general direction).  Fractions un-normalised after.
+template <typename T>
+__device__ __forceinline__ void sstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+                                      Ray<T>& r, T ds) {
+    const T half = T(0.5) * ds;
+    int cu, cv, cw; T tu, tv, tw;
+    auto field = [&](T fu, T fv, T fw) {
+        cell_of(r.iu, fu, C.nu, cu, tu); cell_of(r.iv, fv, C.nv, cv, tv); cell_of(r.iw, fw, C.nw, cw, tw);
+        return trilinear<T>(grid, C.nu, C.plane, cu, cv, cw, tu, tv, tw);
+    };
+    G3<T> g1 = field(r.fu, r.fv, r.fw);
+    T d1u = r.du, d1v = r.dv, d1w = r.dw;
+    T d2u = tfma(half, g1.x, r.du), d2v = tfma(half, g1.y, r.dv), d2w = tfma(half, g1.z, r.dw);
+    G3<T> g2 = field(tfma(half * C.iu_, d1u, r.fu), tfma(half * C.iv_, d1v, r.fv), tfma(half * C.iw_, d1w, r.fw));
+    T d3u = tfma(half, g2.x, r.du), d3v = tfma(half, g2.y, r.dv), d3w = tfma(half, g2.z, r.dw);
+    G3<T> g3 = field(tfma(half * C.iu_, d2u, r.fu), tfma(half * C.iv_, d2v, r.fv), tfma(half * C.iw_, d2w, r.fw));
+    T d4u = tfma(ds, g3.x, r.du), d4v = tfma(ds, g3.y, r.dv), d4w = tfma(ds, g3.z, r.dw);
+    G3<T> g4 = field(tfma(ds * C.iu_, d3u, r.fu), tfma(ds * C.iv_, d3v, r.fv), tfma(ds * C.iw_, d3w, r.fw));
+    const T s6 = ds * T(1.0 / 6.0);
+    r.fu = tfma(s6 * C.iu_, d1u + T(2) * (d2u + d3u) + d4u, r.fu);
+    r.fv = tfma(s6 * C.iv_, d1v + T(2) * (d2v + d3v) + d4v, r.fv);
+    r.fw = tfma(s6 * C.iw_, d1w + T(2) * (d2w + d3w) + d4w, r.fw);
+    r.du = tfma(s6, g1.x + T(2) * (g2.x + g3.x) + g4.x, r.du);
+    r.dv = tfma(s6, g1.y + T(2) * (g2.y + g3.y) + g4.y, r.dv);
+    r.dw = tfma(s6, g1.z + T(2) * (g2.z + g3.z) + g4.z, r.dw);
+    r.s += ds;
+}
+
+// fraction of the chord old -> new at which coordinate (i + f) leaves [0, n-1]; 2 if it does not
+template <typename T>
+__device__ __forceinline__ T leave_fraction(int i, T f_old, T f_new, int n) {
+    T lo = T(-i), hi = T(n - 1 - i);
+    if (f_new < lo) return (lo - f_old) / (f_new - f_old);
+    if (f_new > hi) return (hi - f_old) / (f_new - f_old);
+    return T(2);
+}
+
+template <typename T>
+__device__ __forceinline__ void renorm(int& i, T& f) {
+    T fl = tfloor(f);
+    i += (int)fl;
+    f -= fl;
+}
+// snap a coordinate that should lie on/inside the faces back into [0, n-1]
+template <typename T>
+__device__ __forceinline__ void clamp_in(int& i, T& f, int n) {
+    renorm(i, f);
+    if (i < 0) { i = 0; f = T(0); }
+    if (i > n - 1 || (i == n - 1 && f > T(0))) { i = n - 1; f = T(0); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
+                                                    const double* __restrict__ s0,
+                                                    const uint32_t* __restrict__ perm,
+                                                    double* __restrict__ rf, double* __restrict__ sf,
+                                                    unsigned long long* __restrict__ ray_steps,
+                                                    uint8_t* __restrict__ status, TraceArgs A) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned steps = 0;
+    if (tid < A.np) {
+        const long ray = perm ? (long)perm[tid] : tid;
+        double P[3], D[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            P[k] = s0[(size_t)A.fa[k] * A.np + ray];
+            D[k] = s0[(size_t)(3 + A.fa[k]) * A.np + ray] * (1.0 / kC);
+        }
+        double X[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) X[k] = (P[k] - A.o[k]) / A.h[k];
+
+        int st = 0;
+        double s_acc = 0.0;     // path time spent before/inside the cube
+        // ---- prologue: free flight to the cube if launched outside ------------------------------
+        bool inside = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) inside = inside && X[k] >= 0.0 && X[k] <= (double)(A.n[k] - 1);
+        if (!inside) {
+            double t_in = 0.0, t_out = 1e300;
+            bool hit = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double rate = D[k] / A.h[k], hi = (double)(A.n[k] - 1);
+                if (rate == 0.0) {
+                    hit = hit && X[k] >= 0.0 && X[k] <= hi;
+                } else {
+                    double ta = (0.0 - X[k]) / rate, tb = (hi - X[k]) / rate;
+                    t_in = fmax(t_in, fmin(ta, tb));
+                    t_out = fmin(t_out, fmax(ta, tb));
+                }
+            }
+            hit = hit && t_in <= t_out && t_in < A.s_max;
+            if (hit) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    X[k] += D[k] / A.h[k] * t_in;
+                    X[k] = fmin(fmax(X[k], 0.0), (double)(A.n[k] - 1));
+                }
+                s_acc = t_in;
+            } else {
+                st = TT_RAY_MISSED;
+            }
+        }
+
+        Consts<T> C;
+        C.nu = A.n[0]; C.nv = A.n[1]; C.nw = A.n[2];
+        C.plane = (size_t)A.n[0] * A.n[1];
+        C.ru = (T)(A.h[2] / A.h[0]); C.rv = (T)(A.h[2] / A.h[1]); C.hw = (T)A.h[2];
+        C.iu_ = (T)(1.0 / A.h[0]); C.iv_ = (T)(1.0 / A.h[1]); C.iw_ = (T)(1.0 / A.h[2]);
+
+        Ray<T> r;
+        {
+            double fl;
+            fl = floor(X[0]); r.iu = (int)fl; r.fu = (T)(X[0] - fl);
+            fl = floor(X[1]); r.iv = (int)fl; r.fv = (T)(X[1] - fl);
+            fl = floor(X[2]); r.iw = (int)fl; r.fw = (T)(X[2] - fl);
+        }
+        r.du = (T)D[0]; r.dv = (T)D[1]; r.dw = (T)D[2];
+        r.s = T(0);
+        const T s_left0 = (T)(A.s_max - s_acc);    // path time available inside the cube
+
+        bool alive = (st == 0);
+        bool general = false;
+        const T hsub = T(1) / (T)A.spc;
+
+        // ---- plane marching ---------------------------------------------------------------------
+        if (alive && !(r.dw > T(TT_MARCH_MIN_DW))) general = true;
+        if (alive && !general) {
+            int k = r.iw;
+            T fw = r.fw;
+            int j = (int)(fw * (T)A.spc);          // sub-plane interval index containing fw
+            while (k < C.nw - 1) {
+                T fwb = (j + 1 == A.spc) ? T(1) : (T)(j + 1) * hsub;
+                T h = fwb - fw;
+                Ray<T> old = r;
+                bool ok = zstep<T>(grid, C, r, k, fw, h);
+                ++steps;
+                bool bad = !ok || !(r.dw > T(TT_MARCH_MIN_DW)) || !(r.s <= s_left0);
+                if (bad) {          // hand the step to the general integrator from the old state
+                    r = old; r.iw = k; r.fw = fw; --steps;
+                    general = true;
+                    break;
+                }
+                T lu = leave_fraction(old.iu, old.fu, r.fu, C.nu);
+                T lv = leave_fraction(old.iv, old.fv, r.fv, C.nv);
+                T lam = fmin(lu, lv);
+                if (lam <= T(1)) {   // side exit: re-step to the face, freeze
+                    r = old;
+                    lam = lam < T(0) ? T(0) : lam;
+                    zstep<T>(grid, C, r, k, fw, lam * h);
+                    r.iw = k; r.fw = fw + lam * h;
+                    clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv);
+                    st |= TT_RAY_EXIT_SIDE;
+                    alive = false;
+                    break;
+                }
+                renorm(r.iu, r.fu); renorm(r.iv, r.fv);
+                fw = fwb;
+                if (++j == A.spc) { j = 0; ++k; fw = T(0); }
+            }
+            if (alive && !general) {
+                r.iw = C.nw - 1; r.fw = T(0);
+                st |= TT_RAY_EXIT_FACE;
+                alive = false;
+            }
+        }
+        // ---- general arc-length integrator (steep / backward / time-capped rays) ----------------
+        if (alive && general) {
+            st |= TT_RAY_GENERAL;
+            const T hmin = (T)fmin(A.h[0], fmin(A.h[1], A.h[2]));
+            const T ds0 = hmin * hsub;
+            // a ray sitting on a face and heading out leaves immediately (e.g. probing 'x' launch)
+            for (long it = 0; it < (1L << 40); ++it) {
+                T left = s_left0 - r.s;
+                if (!(left > T(0))) { st |= TT_RAY_TIME_CAP; break; }
+                T ds = ds0 < left ? ds0 : left;
+                Ray<T> old = r;
+                sstep<T>(grid, C, r, ds);
+                ++steps;
+                T lu = leave_fraction(old.iu, old.fu, r.fu, C.nu);
+                T lv = leave_fraction(old.iv, old.fv, r.fv, C.nv);
+                T lw = leave_fraction(old.iw, old.fw, r.fw, C.nw);
+                T lam = fmin(lu, fmin(lv, lw));
+                if (lam <= T(1)) {
+                    bool far_face = (lw <= lu && lw <= lv) && r.fw > old.fw;
+                    r = old;
+                    lam = lam < T(0) ? T(0) : lam;
+                    if (lam > T(0)) sstep<T>(grid, C, r, lam * ds);
+                    clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv); clamp_in(r.iw, r.fw, C.nw);
+                    st |= far_face ? TT_RAY_EXIT_FACE : TT_RAY_EXIT_SIDE;
+                    break;
+                }
+                renorm(r.iu, r.fu); renorm(r.iv, r.fv); renorm(r.iw, r.fw);
+                if (ds < ds0) { st |= TT_RAY_TIME_CAP; break; }
+            }
+            alive = false;
+        }
+
+        // ---- epilogue: ray_at_exit (particle_tracker.py:345-380) and state at time T -------------
+        double Pf[3], Vf[3];
+        if (st & TT_RAY_MISSED) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { Pf[k] = P[k]; Vf[k] = D[k] * kC; }
+            s_acc = 0.0;
+        } else {
+            Pf[0] = A.o[0] + ((double)r.iu + (double)r.fu) * A.h[0];
+            Pf[1] = A.o[1] + ((double)r.iv + (double)r.fv) * A.h[1];
+            Pf[2] = A.o[2] + ((double)r.iw + (double)r.fw) * A.h[2];
+            Vf[0] = (double)r.du * kC; Vf[1] = (double)r.dv * kC; Vf[2] = (double)r.dw * kC;
+            s_acc += (double)r.s;
+        }
+        const double tb = (Pf[2] - A.extent) / Vf[2];
+        rf[0 * A.np + ray] = Pf[0] - Vf[0] * tb;
+        rf[1 * A.np + ray] = atan(Vf[0] / Vf[2]);
+        rf[2 * A.np + ray] = Pf[1] - Vf[1] * tb;
+        rf[3 * A.np + ray] = atan(Vf[1] / Vf[2]);
+        if (sf) {
+            const double t_rest = (A.s_max - s_acc) / kC;   // remaining free flight up to T
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sf[(size_t)A.fa[k] * A.np + ray] = Pf[k] + Vf[k] * t_rest;
+                sf[(size_t)(3 + A.fa[k]) * A.np + ray] = Vf[k];
+            }
+        }
+        if (status) status[ray] = (uint8_t)st;
+    }
+    // ---- ray-step count: warp reduce, one atomic per warp ------------------------------------
+    if (ray_steps) {
+        unsigned v = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
+    }
+}
+
+// ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at arbitrary points,
+// zero outside, faces inclusive (scipy _rgi.py:635-642).
+template <typename T>
+__global__ void dndr_kernel(const typename GridT<T>::V4* __restrict__ grid, TraceArgs A,
+                            const double* __restrict__ pos, long npts, double* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    double g3[3] = {0.0, 0.0, 0.0};
+    double X[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double p = pos[(size_t)A.fa[k] * npts + i];
+        // inclusive faces tested on the physical coordinate, like the reference
+        const double hi = A.o[k] + A.h[k] * (A.n[k] - 1);
+        inside = inside && !(p < A.o[k]) && !(p > hi) && p == p;
+        X[k] = (p - A.o[k]) / A.h[k];
+    }
+    if (inside) {
+        int c[3]; T t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double fl = floor(X[k]);
+            cell_of<T>((int)fl, (T)(X[k] - fl), A.n[k], c[k], t[k]);
+        }
+        G3<T> g = trilinear<T>(grid, A.n[0], (size_t)A.n[0] * A.n[1], c[0], c[1], c[2], t[0], t[1], t[2]);
+        g3[0] = (double)g.x; g3[1] = (double)g.y; g3[2] = (double)g.z;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[(size_t)A.fa[k] * npts + i] = g3[k] * (kC * kC);
+}
+
+static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3],
+                     const double spacing_xyz[3], int par) {
+    TT_REQUIRE(n_xyz && origin_xyz && spacing_xyz, "null geometry pointer");
+    TT_REQUIRE(par >= 0 && par <= 2, "par must be 0, 1 or 2 (got %d)", par);
+    Frame f = frame_of(par);
+    for (int k = 0; k < 3; ++k) {
+        A.fa[k] = f.a[k];
+        A.n[k] = n_xyz[f.a[k]];
+        A.o[k] = origin_xyz[f.a[k]];
+        A.h[k] = spacing_xyz[f.a[k]];
+        TT_REQUIRE(A.n[k] >= 2, "every axis needs >= 2 points");
+        TT_REQUIRE(A.h[k] > 0, "spacing must be > 0");
+    }
+    return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_dev, long np,
+                        const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
+                        unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(p && grid4_dev && s0_dev && rf_dev, "tt_trace: null pointer");
+    TT_REQUIRE(np >= 0, "tt_trace: negative ray count");
+    TT_REQUIRE(p->dtype == TT_F32 || p->dtype == TT_F64, "tt_trace: dtype must be TT_F32 or TT_F64");
+    TT_REQUIRE(p->steps_per_cell >= 1 && p->steps_per_cell <= 1024, "tt_trace: steps_per_cell out of range");
+    TT_REQUIRE(p->s_max > 0 && p->extent == p->extent, "tt_trace: s_max must be > 0");
+    TT_REQUIRE(np < (1L << 32) || !perm_dev, "tt_trace: perm is 32-bit; trace in bundles of < 2^32 rays");
+    TraceArgs A;
+    int rc = fill_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
+    if (rc) return rc;
+    A.extent = p->extent; A.s_max = p->s_max; A.spc = p->steps_per_cell; A.np = np;
+    if (np == 0) return TT_OK;
+    const int block = 128;
+    const long blocks = (np + block - 1) / block;
+    TT_REQUIRE(blocks < (1L << 31), "tt_trace: too many rays for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->dtype == TT_F32)
+        trace_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                               sf_dev, ray_steps_dev, status_dev, A);
+    else
+        trace_kernel<double><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                                sf_dev, ray_steps_dev, status_dev, A);
+    return launch_check("trace_kernel");
+}
+
+extern "C" int tt_dndr(const void* grid4_dev, int grid_dtype, const int n_xyz[3], const double origin_xyz[3],
+                       const double spacing_xyz[3], int par, const double* pos_dev, long npts,
+                       double* out_dev, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(grid4_dev && pos_dev && out_dev, "tt_dndr: null pointer");
+    TT_REQUIRE(grid_dtype == TT_F32 || grid_dtype == TT_F64, "tt_dndr: dtype must be TT_F32 or TT_F64");
+    TraceArgs A;
+    int rc = fill_args(A, n_xyz, origin_xyz, spacing_xyz, par);
+    if (rc) return rc;
+    A.extent = 0; A.s_max = 0; A.spc = 1; A.np = npts;
+    if (npts <= 0) return TT_OK;
+    const int block = 256;
+    const long blocks = (npts + block - 1) / block;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (grid_dtype == TT_F32)
+        dndr_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, A, pos_dev, npts, out_dev);
+    else
+        dndr_kernel<double><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, A, pos_dev, npts, out_dev);
+    return launch_check("dndr_kernel");
+}

@@ -1,0 +1,381 @@
+"""Drop-in mirror of the reference's ``particle_tracker`` module (ElectronCube, dsdt) whose hot
+path runs in hand-written sm_100a CUDA behind the C ABI of ``include/tt_b200.h``.
+
+Reference: particle_tracking/particle_tracker.py (class ElectronCube :121-395, dsdt :398-419).
+Same names, argument meaning and results; what changed underneath:
+
+* ``calc_dndr``   -> one stencil kernel writing an interleaved (g_u, g_v, g_w, ne/nc) grid
+* ``solve``       -> one fused fixed-step RK4 kernel (plane marching, Morton-ordered rays)
+                     instead of scipy ``solve_ivp`` over three ``RegularGridInterpolator`` objects
+* large arrays (``s0``, ``sf``, ``rf``) may live in HBM as :class:`DeviceArray` (numpy-compatible).
+
+Extra, optional keyword arguments (reference-compatible defaults): ``dtype`` ("float32" |
+"float64": arithmetic and grid element type), ``steps_per_cell`` (RK4 sub-planes per grid cell),
+``sort_rays`` (Morton ordering).  There is no CPU fallback: without a CUDA device ``calc_dndr`` /
+``solve`` raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from datetime import datetime
+from time import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceArray, TTError
+
+c = 299792458.0                 # scipy.constants.c, particle_tracker.py:119
+_NC_COEFF = 3.14207787e-4       # particle_tracker.py:228
+_AXIS = {"x": 0, "y": 1, "z": 2}
+UNIFORM_RTOL = 1e-9
+
+
+def _uniform_spacing(a, name):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 1 or a.size < 2:
+        raise ValueError(f"axis {name} must be a 1-D array with at least 2 points")
+    h = (a[-1] - a[0]) / (a.size - 1)
+    if not h > 0:
+        raise ValueError(f"axis {name} must be ascending")
+    dev = np.max(np.abs(np.diff(a) - h))
+    if dev > UNIFORM_RTOL * abs(a[-1] - a[0]):
+        raise NotImplementedError(
+            f"axis {name} is not uniformly spaced (max deviation {dev:.3e} m); the CUDA path "
+            "supports uniform axes only and there is no CPU fallback")
+    return float(a[0]), float(h)
+
+
+class _GradInterp:
+    """Stand-in for the reference's ``dnd?_interp`` RegularGridInterpolator objects
+    (particle_tracker.py:239-241): callable on (N, 3) points, zero outside the cube."""
+
+    def __init__(self, cube, comp):
+        self._cube, self._comp = cube, comp
+
+    def __call__(self, xi):
+        xi = np.asarray(xi, dtype=np.float64)
+        return self._cube.dndr(np.ascontiguousarray(xi.reshape(-1, 3).T))[self._comp].reshape(xi.shape[:-1])
+
+
+class ElectronCube:
+    """A class to hold and generate electron density cubes (particle_tracker.py:121-145)."""
+
+    def __init__(self, x, y, z, probing_direction="z", *, dtype="float32", steps_per_cell=1,
+                 sort_rays=True, keep_sf=True, verbose=True):
+        self.z, self.y, self.x = z, y, x
+        self.extent_x = x.max()
+        self.extent_y = y.max()
+        self.extent_z = z.max()
+        self.probing_direction = probing_direction
+        self.dtype = "float64" if _lib.dtype_code(dtype) == _lib.TT_F64 else "float32"
+        self.steps_per_cell = int(steps_per_cell)
+        self.sort_rays = bool(sort_rays)
+        self.keep_sf = bool(keep_sf)
+        self.verbose = bool(verbose)
+        self._ne = None          # host array or device tensor as supplied
+        self._grid = None        # device tensor [nw, nv, nu, 4]
+        self._s0 = None
+        self.ray_steps = 0       # RK4 steps taken inside the cube by the last solve()
+        self.last_solve_seconds = None
+
+    # ---- geometry -------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return (len(self.x), len(self.y), len(self.z))
+
+    def _geometry(self):
+        ox, hx = _uniform_spacing(self.x, "x")
+        oy, hy = _uniform_spacing(self.y, "y")
+        oz, hz = _uniform_spacing(self.z, "z")
+        return (ox, oy, oz), (hx, hy, hz)
+
+    @property
+    def _par(self):
+        try:
+            return _AXIS[self.probing_direction]
+        except KeyError:
+            raise ValueError("probing_direction must be 'x', 'y' or 'z'") from None
+
+    def _meshgrid(self):
+        return np.meshgrid(self.x, self.y, self.z, indexing="ij")
+
+    XX = property(lambda self: self._meshgrid()[0])
+    YY = property(lambda self: self._meshgrid()[1])
+    ZZ = property(lambda self: self._meshgrid()[2])
+
+    # ---- analytic density set-ups (particle_tracker.py:147-210), evaluated on the device ---------
+    def _axes_dev(self):
+        torch = _lib.torch_cuda()
+        ax = [torch.as_tensor(np.asarray(a, dtype=np.float64), device="cuda") for a in (self.x, self.y, self.z)]
+        return torch, ax[0][:, None, None], ax[1][None, :, None], ax[2][None, None, :]
+
+    def _set_ne_dev(self, t):
+        self._ne = t.expand(*self.shape).contiguous()
+
+    def test_null(self):
+        """Null test, an empty cube (:147-152)."""
+        torch = _lib.torch_cuda()
+        self._ne = torch.zeros(self.shape, dtype=torch.float64, device="cuda")
+
+    def test_slab(self, s=1, n_e0=2e23):
+        """A slab with a linear gradient in x: n_e = n_e0 * (1 + s*x/extent) (:154-165)."""
+        torch, X, Y, Z = self._axes_dev()
+        self._set_ne_dev(n_e0 * (1.0 + s * X / float(self.extent_x)) + 0 * Y + 0 * Z)
+
+    def test_linear_cos(self, s1=0.1, s2=0.1, n_e0=2e23, Ly=1):
+        """Linearly growing sinusoidal perturbation (:167-177)."""
+        torch, X, Y, Z = self._axes_dev()
+        self._set_ne_dev(n_e0 * (1.0 + s1 * X / float(self.extent_x)) * (1 + s2 * torch.cos(2 * np.pi * Y / Ly)) + 0 * Z)
+
+    def test_exponential_cos(self, n_e0=1e24, Ly=1e-3, s=2e-3):
+        """Exponentially growing sinusoidal perturbation (:179-188)."""
+        torch, X, Y, Z = self._axes_dev()
+        self._set_ne_dev(n_e0 * 10 ** (X / s) * (1 + torch.cos(2 * np.pi * Y / Ly)) + 0 * Z)
+
+    def test_lens(self, n_e0=1e24, LR=1e-3):
+        """Normal distribution with axis along z (:190-199)."""
+        torch, X, Y, Z = self._axes_dev()
+        self._set_ne_dev(n_e0 * torch.exp(-(X**2 + Y**2) / LR**2) + 0 * Z)
+
+    def test_liner(self, n_e0=1e24, LR=1e-3):
+        """Normal distribution with axis along y (:201-210)."""
+        torch, X, Y, Z = self._axes_dev()
+        self._set_ne_dev(n_e0 * torch.exp(-(X**2 + Z**2) / LR**2) + 0 * Y)
+
+    def external_ne(self, ne):
+        """Load externally generated grid (:212-218): numpy array, torch tensor or DeviceArray of
+        shape (len(x), len(y), len(z)), density in m^-3."""
+        self._ne = ne.torch if isinstance(ne, DeviceArray) else ne
+
+    @property
+    def ne(self):
+        if self._ne is None:
+            raise AttributeError("ne not set: call a test_* method or external_ne first")
+        if isinstance(self._ne, np.ndarray):
+            return self._ne
+        return self._ne.detach().cpu().numpy()
+
+    @ne.setter
+    def ne(self, v):
+        self.external_ne(v)
+
+    # ---- gradient grid ----------------------------------------------------------------------------
+    def calc_dndr(self, lwl=1053e-9, ne_max=1):
+        """Generate the gradient grid (replaces the interpolators of :220-241).
+
+        omega = 2 pi c / lwl, nc = 3.14207787e-4 omega^2, ne/nc clipped at ne_max, gradients by
+        central differences (one-sided on the faces)."""
+        torch = _lib.torch_cuda()
+        lib = _lib.load()
+        if self._ne is None:
+            raise AttributeError("ne not set: call a test_* method or external_ne first")
+        self.omega = 2 * np.pi * (c / lwl)
+        self.nc = _NC_COEFF * self.omega**2
+        self.ne_max = ne_max
+        origin, spacing = self._geometry()
+        ne = self._ne
+        if tuple(ne.shape) != self.shape:
+            raise ValueError(f"ne has shape {tuple(ne.shape)}, expected {self.shape}")
+        if isinstance(ne, np.ndarray) and ne.dtype not in (np.float32, np.float64):
+            ne = ne.astype(np.float64)
+        ne_dev = _lib.to_device(ne)
+        if ne_dev.dtype not in (torch.float32, torch.float64):
+            ne_dev = ne_dev.to(torch.float64)
+        gdt = torch.float64 if self.dtype == "float64" else torch.float32
+        par = self._par
+        fa = {2: (0, 1, 2), 1: (0, 2, 1), 0: (1, 2, 0)}[par]
+        n = self.shape
+        grid = torch.empty((n[fa[2]], n[fa[1]], n[fa[0]], 4), dtype=gdt, device="cuda")
+        _lib.check(lib.tt_calc_dndr(_lib.ptr(ne_dev), _lib.dtype_code(ne_dev.dtype), _lib.i3(n), _lib.d3(spacing),
+                                    par, float(self.nc), float(ne_max), _lib.ptr(grid),
+                                    _lib.dtype_code(gdt), _lib.stream_ptr()), "tt_calc_dndr")
+        self._grid, self._frame, self._origin, self._spacing = grid, fa, origin, spacing
+        self.dndx_interp, self.dndy_interp, self.dndz_interp = (_GradInterp(self, k) for k in range(3))
+
+    def _require_grid(self):
+        if self._grid is None:
+            raise AttributeError("gradient grid not built: call calc_dndr() first")
+        return self._grid
+
+    def _grid_component(self, axis):
+        """(nx, ny, nz) FP64 numpy cube of frame component holding xyz axis `axis` (or ne/nc)."""
+        g = self._require_grid()
+        comp = 3 if axis == 3 else self._frame.index(axis)
+        # grid dims are (w, v, u): xyz axis a sits at grid dim 2 - frame.index(a)
+        dims = [2 - self._frame.index(a) for a in (0, 1, 2)]
+        return g[..., comp].permute(*dims).double().cpu().numpy()
+
+    ne_nc = property(lambda self: self._grid_component(3))
+    dndx = property(lambda self: self._grid_component(0) * c**2)
+    dndy = property(lambda self: self._grid_component(1) * c**2)
+    dndz = property(lambda self: self._grid_component(2) * c**2)
+
+    def dndr(self, x):
+        """Gradient at the locations x (3 x N, metres) -> 3 x N, zero outside the cube (:243-256)."""
+        torch = _lib.torch_cuda()
+        lib = _lib.load()
+        g = self._require_grid()
+        host = not isinstance(x, (DeviceArray, torch.Tensor))
+        xd = _lib.to_device(x, torch.float64)
+        if xd.dim() != 2 or xd.shape[0] != 3:
+            raise ValueError("x must have shape (3, N)")
+        out = torch.empty_like(xd)
+        _lib.check(lib.tt_dndr(_lib.ptr(g), _lib.dtype_code(g.dtype), _lib.i3(self.shape), _lib.d3(self._origin),
+                               _lib.d3(self._spacing), self._par, _lib.ptr(xd), xd.shape[1], _lib.ptr(out),
+                               _lib.stream_ptr()), "tt_dndr")
+        return out.cpu().numpy() if host else DeviceArray(out)
+
+    # ---- beam ---------------------------------------------------------------------------------------
+    def init_beam(self, Np, beam_size, divergence, *, seed=None, first_ray=0):
+        """Launch rays s0 (6 x Np): uniform disc of radius beam_size on the entry face, Gaussian
+        divergence (:258-310).
+
+        Default (``seed=None``): drawn on the host from numpy's global RNG in the reference's draw
+        order, i.e. bit-identical to the reference after ``np.random.seed``.  With ``seed`` the rays
+        are generated on the device (Philox counter RNG, ray ids first_ray .. first_ray+Np) and stay
+        in HBM."""
+        par = self._par
+        self.extent = (self.extent_x, self.extent_y, self.extent_z)[par]
+        Np = int(Np)
+        if seed is not None:
+            torch = _lib.torch_cuda()
+            s0 = torch.empty((6, Np), dtype=torch.float64, device="cuda")
+            _lib.check(_lib.load().tt_init_beam(Np, int(first_ray), int(seed), float(beam_size), float(divergence),
+                                                float(self.extent), par, _lib.ptr(s0), _lib.stream_ptr()),
+                       "tt_init_beam")
+            self._s0 = DeviceArray(s0)
+            return
+        s0 = np.zeros((6, Np))
+        t = 2 * np.pi * np.random.rand(Np)
+        u = np.random.rand(Np) + np.random.rand(Np)
+        u[u > 1] = 2 - u[u > 1]
+        phi = np.pi * np.random.rand(Np)
+        chi = divergence * np.random.randn(Np)
+        t1, t2 = {2: (0, 1), 1: (0, 2), 0: (1, 2)}[par]
+        s0[t1] = beam_size * u * np.cos(t)
+        s0[t2] = beam_size * u * np.sin(t)
+        s0[par] = self.extent if par == 0 else -self.extent    # 'x' launches at +extent (:287)
+        s0[3 + t1] = c * np.sin(chi) * np.cos(phi)
+        s0[3 + t2] = c * np.sin(chi) * np.sin(phi)
+        s0[3 + par] = c * np.cos(chi)
+        self._s0 = s0
+
+    @property
+    def s0(self):
+        return self._s0
+
+    @s0.setter
+    def s0(self, v):
+        self._s0 = v
+
+    # ---- solve ----------------------------------------------------------------------------------------
+    def solve(self, method="RK45", *, return_status=False):
+        """Trace all rays of ``self.s0`` through the cube and return rf (4 x Np: p1, angle1, p2,
+        angle2 on the exit plane), as :312-331.  ``method`` is accepted for compatibility; the
+        integrator is the fixed-step RK4 kernel.  Sets ``sf`` (state at t = sqrt(8) extent / c),
+        ``rf``, ``ray_steps``."""
+        torch = _lib.torch_cuda()
+        lib = _lib.load()
+        grid = self._require_grid()
+        if not isinstance(method, str):      # stale call style solve(ss) of the example scripts
+            self._s0 = method
+        if self._s0 is None:
+            raise AttributeError("s0 not set: call init_beam() first")
+        if not hasattr(self, "extent"):
+            self.extent = (self.extent_x, self.extent_y, self.extent_z)[self._par]
+        s0 = _lib.to_device(self._s0, torch.float64)
+        if s0.dim() != 2 or s0.shape[0] != 6:
+            raise ValueError("s0 must have shape (6, Np)")
+        Np = s0.shape[1]
+        stream = _lib.stream_ptr()
+        start = time()
+        perm = None
+        if self.sort_rays and Np > 1:
+            need = C.c_size_t(0)
+            _lib.check(lib.tt_sort_rays_workspace(Np, C.byref(need)), "tt_sort_rays_workspace")
+            ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+            perm = torch.empty(Np, dtype=torch.int32, device="cuda")
+            _lib.check(lib.tt_sort_rays(_lib.ptr(s0), Np, self._par, _lib.d3(self._origin), _lib.d3(self._spacing),
+                                        _lib.i3(self.shape), _lib.ptr(perm), _lib.ptr(ws), need.value, stream),
+                       "tt_sort_rays")
+        p = _lib.TraceParams()
+        p.n_xyz[:] = self.shape
+        p.origin_xyz[:] = self._origin
+        p.spacing_xyz[:] = self._spacing
+        p.par = self._par
+        p.extent = float(self.extent)
+        p.s_max = float(np.sqrt(8.0) * self.extent)
+        p.steps_per_cell = self.steps_per_cell
+        p.dtype = _lib.dtype_code(grid.dtype)
+        p.variant = int(getattr(self, "kernel_variant", 0))
+        rf = torch.empty((4, Np), dtype=torch.float64, device="cuda")
+        sf = torch.empty((6, Np), dtype=torch.float64, device="cuda") if self.keep_sf else None
+        steps = torch.zeros(1, dtype=torch.int64, device="cuda")
+        status = torch.empty(Np, dtype=torch.uint8, device="cuda") if return_status else None
+        _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0), Np, _lib.ptr(perm), _lib.ptr(rf),
+                                _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
+        self._perm = perm
+        if self.verbose:
+            torch.cuda.current_stream().synchronize()
+            self.last_solve_seconds = time() - start
+            print("Ray trace completed in:\t", self.last_solve_seconds, "s")
+        self._steps_dev = steps
+        self.sf = DeviceArray(sf) if sf is not None else None
+        self.rf = DeviceArray(rf)
+        self.rf.perm = perm        # lets the detectors visit the rays in Morton order
+        self.status = DeviceArray(status) if status is not None else None
+        return self.rf
+
+    @property
+    def ray_steps(self):
+        d = getattr(self, "_steps_dev", None)
+        return int(d.item()) if d is not None else 0
+
+    @ray_steps.setter
+    def ray_steps(self, v):
+        self._steps_dev = None
+
+    def ray_at_exit(self):
+        """rf from ``self.sf`` by linear back-projection to the plane axis = +extent (:333-380)."""
+        torch = _lib.torch_cuda()
+        sf = _lib.to_device(self.sf, torch.float64)
+        par = self._par
+        t1, t2 = {2: (0, 1), 1: (0, 2), 0: (1, 2)}[par]
+        tb = (sf[par] - float(self.extent)) / sf[3 + par]
+        rf = torch.stack([sf[t1] - sf[3 + t1] * tb, torch.atan(sf[3 + t1] / sf[3 + par]),
+                          sf[t2] - sf[3 + t2] * tb, torch.atan(sf[3 + t2] / sf[3 + par])])
+        return DeviceArray(rf)
+
+    def save_output_rays(self, fn=None):
+        """Save rf as .npy, auto-named by date and time (:382-395)."""
+        if fn is None:
+            fn = "{} rays.npy".format(datetime.now().strftime("%Y-%m-%d_%H-%M-%S"))
+        else:
+            fn = "{}.npy".format(fn)
+        with open(fn, "wb") as f:
+            np.save(f, np.asarray(self.rf))
+
+    # stale-API helper still called by the reference's example scripts (example_MPI.py:62,111)
+    def clear_memory(self):
+        self._ne = None
+
+
+def dsdt(t, s, ElectronCube):
+    """ODE right-hand side [v ; dndr(x)] on the flattened 6N state (:398-419).  Kept for API
+    parity (the CUDA integrator does not call it); evaluates the gradient on the device."""
+    Np = s.size // 6
+    s = np.asarray(s).reshape(6, Np)
+    sprime = np.zeros_like(s)
+    sprime[3:6, :] = np.asarray(ElectronCube.dndr(np.ascontiguousarray(s[:3, :])))
+    sprime[:3, :] = s[3:, :]
+    return sprime.flatten()
+
+
+def init_beam(Np, beam_size, divergence, ne_extent, probing_direction="z"):
+    """Module-level variant used by the reference's (stale) example scripts
+    (example_MPI.py:57, example_kitchensink.py:89): returns s0 instead of storing it."""
+    ax = np.array([-ne_extent, ne_extent])
+    cube = ElectronCube(ax, ax, ax, probing_direction)
+    cube.init_beam(Np, beam_size, divergence)
+    return cube.s0

@@ -1,0 +1,325 @@
+"""Drop-in mirror of the reference's ``ray_transfer_matrix`` module: optical element functions,
+``Rays`` and the Shadowgraphy / Schlieren_DF / Schlieren_LF / AFR detectors.
+
+Reference: particle_tracking/ray_transfer_matrix.py (elements :37-154, Rays :156-206, detectors
+:208-299).  Every element chain and the histogram run in ONE fused CUDA kernel
+(csrc/optics_hist.cu) instead of one numpy temporary per element; a detector's ``solve()`` only
+records its element program, the kernel runs when ``rf`` or ``histogram()`` is first needed.
+
+Rays are 4 x N arrays (x, theta, y, phi); numpy arrays, torch tensors and DeviceArray are accepted.
+Rejected rays are NaN in all four rows, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DeviceArray
+
+__all__ = ["m_to_mm", "lens", "sym_lens", "distance", "circular_aperture", "circular_stop", "annular_stop",
+           "angular_filter", "rect_aperture", "knife_edge", "plot_afr", "Rays", "Shadowgraphy", "Schlieren_DF",
+           "Schlieren_LF", "AFR"]
+
+
+# ---- element programs ---------------------------------------------------------------------------
+def _op(code, a=0.0, b=0.0):
+    return (int(code), float(a), float(b))
+
+
+def _op_distance(d):
+    return _op(_lib.OP_DISTANCE, d)
+
+
+def _op_lens(f1, f2):
+    return _op(_lib.OP_LENS, f1, f2)
+
+
+def _op_knife(offset, axis, direction):
+    if axis not in ("x", "y"):
+        raise ValueError("axis must be 'x' or 'y'")
+    if direction == 0:
+        raise ValueError("Direction must be <0 or >0")
+    return _op(_lib.OP_KNIFE_EDGE, offset, (1.0 if axis == "x" else 2.0) * (1.0 if direction > 0 else -1.0))
+
+
+def _ops_angular_filter(Rs):
+    Rs = np.asarray(Rs, dtype=np.float64)
+    return [_op(_lib.OP_ANNULAR_STOP, Rs[2 * i], Rs[2 * i + 1]) for i in range(len(Rs) // 2)]
+
+
+def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True):
+    """Launch the fused kernel.  hist = (xedges_dev, yedges_dev, H_dev) or None."""
+    torch = _lib.torch_cuda()
+    lib = _lib.load()
+    if r_dev.dim() != 2 or r_dev.shape[0] != 4:
+        raise NotImplementedError("ray arrays must have shape (4, N): x, theta, y, phi")
+    if len(program) > _lib.MAX_OPTICS:
+        raise ValueError(f"element program longer than {_lib.MAX_OPTICS}")
+    n = r_dev.shape[1]
+    prog = (_lib.Optic * max(1, len(program)))()
+    for k, (code, a, b) in enumerate(program):
+        prog[k].op, prog[k].a, prog[k].b = code, a, b
+    out = torch.empty_like(r_dev) if want_rf else None
+    xe = ye = H = None
+    nbx = nby = 0
+    if hist is not None:
+        xe, ye, H = hist
+        nbx, nby = xe.numel() - 1, ye.numel() - 1
+    _lib.check(lib.tt_optics_hist_perm(_lib.ptr(r_dev), n, _lib.ptr(perm), float(pos_scale), prog, len(program),
+                                       _lib.ptr(xe), nbx, _lib.ptr(ye), nby, _lib.ptr(H), _lib.ptr(out),
+                                       _lib.stream_ptr()), "tt_optics_hist")
+    return out
+
+
+def _apply(r, program, inplace=False):
+    """Apply an element program to a user array, returning the same kind of array."""
+    torch = _lib.torch_cuda()
+    dev = _lib.to_device(r, torch.float64)
+    out = _run(dev, program)
+    if isinstance(r, DeviceArray):
+        if inplace:
+            r.torch.copy_(out)
+            r._np = None
+            return r
+        return DeviceArray(out)
+    if isinstance(r, torch.Tensor):
+        if inplace:
+            r.copy_(out.to(r.device, r.dtype))
+            return r
+        return out
+    res = out.cpu().numpy()
+    if inplace:
+        r[...] = res
+        return r
+    return res
+
+
+def m_to_mm(r):
+    """Copy with positions (rows 0, 2) scaled m -> mm (:37-40)."""
+    if isinstance(r, DeviceArray) or not isinstance(r, np.ndarray):
+        torch = _lib.torch_cuda()
+        t = _lib.to_device(r, torch.float64).clone()
+        t[0::2] *= 1e3
+        return DeviceArray(t)
+    rr = np.ndarray.copy(r)
+    rr[0::2, :] *= 1e3
+    return rr
+
+
+def lens(r, f1, f2):
+    """Thin lens, focal lengths f1 and f2 in the two orthogonal axes (:42-54)."""
+    return _apply(r, [_op_lens(f1, f2)])
+
+
+def sym_lens(r, f):
+    """Axisymmetric lens (:56-60)."""
+    return lens(r, f, f)
+
+
+def distance(r, d):
+    """Free-space propagation over d (:62-71)."""
+    return _apply(r, [_op_distance(d)])
+
+
+def circular_aperture(r, R):
+    """Rejects rays outside radius R, in place (:73-79)."""
+    return _apply(r, [_op(_lib.OP_CIRC_APERTURE, R)], inplace=True)
+
+
+def circular_stop(r, R):
+    """Rejects rays inside radius R, in place (:81-87)."""
+    return _apply(r, [_op(_lib.OP_CIRC_STOP, R)], inplace=True)
+
+
+def annular_stop(r, R1, R2):
+    """Boolean mask of the rays that fall between R1 and R2 (:89-97); r is not modified."""
+    torch = _lib.torch_cuda()
+    dev = _lib.to_device(r, torch.float64)
+    out = _run(dev, [_op(_lib.OP_ANNULAR_STOP, R1, R2)])
+    mask = torch.isnan(out[0]) & ~torch.isnan(dev[0])
+    return mask if isinstance(r, (torch.Tensor, DeviceArray)) else mask.cpu().numpy()
+
+
+def angular_filter(r, Rs):
+    """Rejects rays inside the annuli (Rs[0],Rs[1]), (Rs[2],Rs[3]), ..., in place (:99-111)."""
+    return _apply(r, _ops_angular_filter(Rs), inplace=True)
+
+
+def rect_aperture(r, Lx, Ly):
+    """Rejects rays outside a 2Lx x 2Ly rectangle in BOTH axes, in place (:128-136)."""
+    return _apply(r, [_op(_lib.OP_RECT_APERTURE, Lx, Ly)], inplace=True)
+
+
+def knife_edge(r, offset, axis, direction):
+    """Knife edge in 'x' or 'y'; direction > 0 rejects above the offset, < 0 below (:138-154)."""
+    return _apply(r, [_op_knife(offset, axis, direction)], inplace=True)
+
+
+def plot_afr(Rs):
+    """Plot the angular filter (:113-126).  matplotlib is imported lazily (plotting is outside the
+    CUDA path)."""
+    import matplotlib as mpl
+    import matplotlib.pyplot as plt
+    fig, ax = plt.subplots(figsize=(4, 4), dpi=200)
+    for i in range(0, len(Rs) // 2):
+        R1, R2 = Rs[2 * i], Rs[2 * i + 1]
+        dR = R2 - R1
+        an = mpl.patches.Circle((0, 0), R2) if dR >= R2 else mpl.patches.Annulus((0, 0), R2, dR)
+        ax.add_patch(an)
+    ax.set_xlim([-Rs.max(), Rs.max()])
+    ax.set_ylim([-Rs.max(), Rs.max()])
+    return fig, ax
+
+
+# ---- detectors --------------------------------------------------------------------------------------
+class Rays:
+    """Inheritable class for ray diagnostics (:156-206)."""
+
+    def __init__(self, r0, focal_plane=0, L=400, R=25, Lx=18, Ly=13.5):
+        """r0: 4 x N rays [x, theta, y, phi] in m / rad; L: length scale (first lens at L), R: lens
+        radius, Lx, Ly: detector size in mm (:160-172)."""
+        self.focal_plane, self.L, self.R, self.Lx, self.Ly = focal_plane, L, R, Lx, Ly
+        torch = _lib.torch_cuda()
+        self._perm = getattr(r0, "perm", None)
+        self._r0_m = _lib.to_device(r0, torch.float64)      # metres; m_to_mm happens in the kernel
+        self._r0_mm = None
+        self._program = None
+        self._rf = None
+        self.H_dev = None
+
+    # r0 in mm, as the reference stores it (:172)
+    @property
+    def r0(self):
+        if self._r0_m is None:
+            return None
+        if self._r0_mm is None:
+            t = self._r0_m.clone()
+            t[0::2] *= 1e3
+            self._r0_mm = DeviceArray(t)
+        return self._r0_mm
+
+    @r0.setter
+    def r0(self, v):
+        if v is None:
+            self._r0_m = self._r0_mm = None
+            return
+        torch = _lib.torch_cuda()
+        t = _lib.to_device(v, torch.float64).clone()
+        t[0::2] *= 1e-3
+        self._r0_m, self._r0_mm = t, None
+
+    def _set_program(self, program):
+        self._program = list(program)
+        self._rf = None
+
+    @property
+    def rf(self):
+        if self._rf is None and self._program is not None and self._r0_m is not None:
+            self._rf = DeviceArray(_run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm))
+        return self._rf
+
+    @rf.setter
+    def rf(self, v):
+        self._rf = v if (v is None or isinstance(v, DeviceArray)) else DeviceArray(_lib.to_device(v))
+        if v is None:
+            self._program = None
+
+    def histogram(self, bin_scale=10, pix_x=3448, pix_y=2574, clear_mem=False):
+        """Bin detector-plane rays; defaults are for a KAF-8300 (:173-195).  Sets ``H``
+        (pix_y//bin_scale, pix_x//bin_scale) float64 like numpy.histogram2d(...).T, ``xedges``,
+        ``yedges``; ``H_dev`` keeps the integer counts on the device (for NCCL all-reduce)."""
+        torch = _lib.torch_cuda()
+        nbx, nby = pix_x // bin_scale, pix_y // bin_scale
+        # numpy.histogramdd builds its edges with linspace(range_min, range_max, bins + 1)
+        self.xedges = np.linspace(-self.Lx / 2, self.Lx / 2, nbx + 1)
+        self.yedges = np.linspace(-self.Ly / 2, self.Ly / 2, nby + 1)
+        xe = torch.from_numpy(self.xedges).cuda()
+        ye = torch.from_numpy(self.yedges).cuda()
+        H = torch.zeros((nby, nbx), dtype=torch.int64, device="cuda")
+        if self._rf is not None:                      # rays already at the detector plane
+            _run(self._rf.torch, [], perm=self._perm, hist=(xe, ye, H), want_rf=False)
+        elif self._program is not None and self._r0_m is not None:   # fused: optics + binning, one pass
+            _run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm, hist=(xe, ye, H), want_rf=False)
+        else:
+            raise AttributeError("no rays to bin: call solve() first")
+        self.H_dev = H
+        self.H = H.double().cpu().numpy()
+        if clear_mem:
+            self.clear_rays()
+
+    def plot(self, ax, clim=None, cmap=None):
+        ax.imshow(self.H, interpolation="nearest", origin="lower", clim=clim, cmap=cmap,
+                  extent=[self.xedges[0], self.xedges[-1], self.yedges[0], self.yedges[-1]])
+
+    def clear_rays(self):
+        """Clears the r0 and rf variables to save memory (:201-206)."""
+        self._r0_m = self._r0_mm = None
+        self._rf = None
+        self._program = None
+        self._perm = None
+
+    def __getstate__(self):          # detectors stay picklable (example_MPI.py:152-166)
+        d = dict(self.__dict__)
+        for k in ("_r0_m", "_r0_mm", "_rf", "_perm", "H_dev"):
+            v = d.get(k)
+            if v is not None:
+                d[k] = np.asarray(v.cpu() if hasattr(v, "cpu") else v)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        for k in ("_r0_mm", "_rf"):
+            if isinstance(d.get(k), np.ndarray):
+                self.__dict__[k] = None
+        for k in ("_r0_m", "_perm", "H_dev"):
+            self.__dict__[k] = None if not isinstance(d.get(k), np.ndarray) else d[k]
+
+
+class Shadowgraphy(Rays):
+    """Two-lens M = 1 telescope, apertures of radius R at both lenses (:208-227)."""
+
+    def solve(self):
+        L, R = self.L, self.R
+        self._set_program([
+            _op_distance(L - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, R), _op_lens(L, L),
+            _op_distance(L * 2),
+            _op(_lib.OP_CIRC_APERTURE, R), _op_lens(L, L),
+            _op_distance(L)])
+
+
+class Schlieren_DF(Rays):
+    """Dark-field schlieren: circular stop of radius R [mm] at the focal plane (:229-250)."""
+
+    def solve(self, R=1):
+        L, Ra = self.L, self.R
+        self._set_program([
+            _op_distance(L - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L, L),
+            _op_distance(L), _op(_lib.OP_CIRC_STOP, R),
+            _op_distance(L), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L, L),
+            _op_distance(L)])
+
+
+class Schlieren_LF(Rays):
+    """Light-field schlieren: circular aperture of radius R [mm] at the focal plane (:252-273)."""
+
+    def solve(self, R=1):
+        L, Ra = self.L, self.R
+        self._set_program([
+            _op_distance(L - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L, L),
+            _op_distance(L), _op(_lib.OP_CIRC_APERTURE, R),
+            _op_distance(L), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L, L),
+            _op_distance(L)])
+
+
+class AFR(Rays):
+    """Angular filter refractometer: annular stops Rs at the focal plane (:275-299)."""
+
+    def solve(self, Rs):
+        L, Ra = self.L, self.R
+        self._set_program([
+            _op_distance(L / 2 - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L / 2, L / 2),
+            _op_distance(L / 4), *_ops_angular_filter(Rs),
+            _op_distance(L / 4), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L / 2, L / 2),
+            _op_distance(L / 2)])
