@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-integration hot path (BASELINE.json metric: ray-steps/s and rays/s for rays
+through a Gaussian-random ne cube on B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one bundle of rays: calc_dndr (ne cube -> float4 gradient
+grid), Morton sort of the launch rays, the RK4 trace kernel, Shadowgraphy optics + histogram, and
+(N > 1) the NCCL all-reduce of the histogram.  Rays are sharded per rank (weak scaling: every GPU
+traces RAYS rays), the ne cube is broadcast from rank 0 once.
+
+  value : whole-job ray-steps/s with inputs (ne cube, launch rays) resident in HBM
+  e2e   : the same metric through the public Python API with HOST (pinned) numpy buffers in and the
+          histogram + ray-step count read back to the host inside the timed region
+  roofline : trace kernel, algorithmic bytes = 512 B per ray-step (4 stages x 8 corners x 16 B,
+          SURVEY section 8d) over the kernel's CUDA-event duration, against the measured HBM copy
+          bandwidth of MEASURED_PEAKS.json
+  cpu_baseline : the reference's scipy path (oracle port: solve_ivp RK45 at default tolerances over
+          RegularGridInterpolator, multiprocessing.Pool over ray bundles as example_multiprocess.py)
+          on a bounded sample of the same cube, on this box's host cores
+
+--impl reference times that CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_RAY_STEP = 512      # 4 RK4 stages x 8 trilinear corners x 16 B (float4), FP32 mode
+WORKLOADS = {
+    # name: (N_half of gaussian3D_FFT -> M = 2N+1 points per axis, rays per GPU, BASELINE config)
+    "c3": (256, 100_000_000, "configs[2]: 513^3 (gaussian3D_FFT N=256) k^-11/3 GRF ne cube, 1e8 rays per GPU, shadowgraphy"),
+    "c2": (128, 10_000_000, "configs[1]: 257^3 (gaussian3D_FFT N=128) k^-11/3 GRF ne cube, 1e7 rays per GPU, shadowgraphy"),
+    "c1": (32, 100_000, "smoke-size: 65^3 GRF cube, 1e5 rays"),
+}
+BEAM_SIZE, DIVERGENCE, EXTENT, LWL = 4e-3, 0.05e-3, 5e-3, 1053e-9
+SPECTRUM = lambda k: k ** (-11.0 / 3.0)          # noqa: E731
+
+
+def ne_from_field(f, xp):
+    """ne = 1e25 * clip(1 + 0.3 f / sigma, 0): mean 1 % of nc, 30 % rms."""
+    return 1e25 * xp.clip(1 + 0.3 * f / f.std(), 0, None)
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.p, self.path = index, None, f"/tmp/tt_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+_CPU = {}
+
+
+def _cpu_worker(args):
+    """One Pool worker = one bundle, as example_multiprocess.py:41-51: seed, init_beam, solve (scipy
+    RK45, default tolerances), shadowgraphy histogram."""
+    from oracle import ref_numpy as orc
+    i, n = args
+    np.random.seed(1000 + i)
+    s0 = orc.init_beam(n, BEAM_SIZE, DIVERGENCE, EXTENT, "z")
+    rf, sf, nfev = orc.solve(_CPU["field"], s0, EXTENT, "z")
+    H, _, _ = orc.histogram(orc.detector("shadowgraphy", rf))
+    return n, nfev, H.sum()
+
+
+def host_grf_cube(n_half, seed=7):
+    """Host-side synthetic ne cube of the same statistics (k^-11/3 GRF, M = 2N+1) for the CPU arm when
+    no device cube is available: white noise shaped in Fourier space (scipy.fft, all host threads)."""
+    import scipy.fft as sfft
+    M = 2 * n_half + 1
+    rng = np.random.default_rng(seed)
+    w = rng.standard_normal((M, M, M), dtype=np.float32)
+    F = sfft.rfftn(w, workers=-1)
+    k = np.fft.fftfreq(M)
+    kz = np.fft.rfftfreq(M)
+    K2 = (k[:, None, None] ** 2 + k[None, :, None] ** 2 + kz[None, None, :] ** 2).astype(np.float32)
+    K2[0, 0, 0] = 1.0
+    F *= K2 ** (-11.0 / 12.0)          # sqrt(k^-11/3)
+    F[0, 0, 0] = 0
+    f = sfft.irfftn(F, s=(M, M, M), workers=-1)
+    return ne_from_field(f.astype(np.float64), np)
+
+
+def cpu_reference_setup(ne_host, M):
+    from oracle import ref_numpy as orc
+    x = np.linspace(-EXTENT, EXTENT, M)
+    _CPU["field"] = orc.make_field(ne_host, x, x, x, LWL)
+
+
+def cpu_reference_step(rays_per_worker, cores):
+    """Returns dict(rays, ray_rhs_evals, seconds) for one bounded sample over `cores` processes."""
+    import multiprocessing as mp
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"                      # pinned: oversubscription costs 3x
+    ctx = mp.get_context("fork")                 # cube built once before the fork (copy-on-write)
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_cpu_worker, [(i, rays_per_worker) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    return {"rays": sum(o[0] for o in out), "ray_rhs_evals": sum(o[1] for o in out), "seconds": dt}
+
+
+def cpu_line_fields(res, cores, rays_per_worker, M, kind="port"):
+    steps = res["ray_rhs_evals"] / 4.0           # 4 RHS evaluations = 1 RK4-equivalent ray-step
+    return {"value": steps / res["seconds"], "unit": "ray-steps/s", "cores": cores, "kind": kind,
+            "rays_per_s": res["rays"] / res["seconds"],
+            "sample": f"{cores} processes x {rays_per_worker} rays on the same {M}^3 cube; scipy RK45 default "
+                      f"rtol=1e-3 (reference ElectronCube.solve), ray-steps = nfev*rays/4; {res['seconds']:.1f} s"}
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's CPU implementation alone, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n_half, _, desc = WORKLOADS[wl]
+    M = 2 * n_half + 1
+    cores = os.cpu_count() or 1
+    rays_per_worker = args.cpu_rays
+    if args.cube_file:                     # the GPU arm's own cube (cpu_baseline leg)
+        ne = np.load(args.cube_file).astype(np.float64)
+        M = ne.shape[0]
+    else:
+        ne = host_grf_cube(n_half)
+    cpu_reference_setup(ne, M)
+    del ne
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(max(rays_per_worker // 4, 50), cores)
+    tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0}
+    for _ in range(args.steps):
+        r = cpu_reference_step(rays_per_worker, cores)
+        for k in tot:
+            tot[k] += r[k]
+    cb = cpu_line_fields(tot, cores, rays_per_worker, M)
+    line = {"metric": "ray-steps/s", "value": cb["value"], "unit": "ray-steps/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "rays_per_s": cb["rays_per_s"],
+            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": cores * rays_per_worker},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args, wl):
+    import torch
+    from turbulence_tracing_b200 import distributed as ttd
+    from turbulence_tracing_b200 import particle_tracker as pt, ray_transfer_matrix as rtm, turboGen as tg
+    from turbulence_tracing_b200 import _lib
+
+    rank, world, local = ttd.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    _lib.load(build_if_missing=False)
+    n_half, rays, desc = WORKLOADS[wl]
+    if args.rays:
+        rays = args.rays
+    M = 2 * n_half + 1
+    x = np.linspace(-EXTENT, EXTENT, M)
+    dtype = args.dtype
+
+    # ---- synthetic inputs: GRF cube on rank 0 (device Philox + cuFFT), NCCL broadcast ------------
+    t0 = time.perf_counter()
+    ne = torch.empty((M, M, M), dtype=torch.float32, device=dev)
+    if rank == 0:
+        f = tg.gaussian3D_FFT(n_half, SPECTRUM, seed=1234, dtype="float32", return_device=True).torch
+        ne.copy_(ne_from_field(f, torch))
+        del f
+    ttd.broadcast_cube(ne, src=0)
+    torch.cuda.synchronize()
+    t_cube = time.perf_counter() - t0
+
+    def make_cube():
+        c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=args.steps_per_cell, keep_sf=False, verbose=False)
+        c.kernel_variant = args.variant
+        return c
+
+    cube = make_cube()
+    first, _ = ttd.shard_range(rays * world, rank, world)       # weak scaling: `rays` per rank
+    cube.external_ne(ne)
+    cube.init_beam(rays, BEAM_SIZE, DIVERGENCE, seed=99, first_ray=first)
+    s0_dev = cube.s0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    trace_ms = []
+
+    def step_device():
+        cube.external_ne(ne)
+        cube.calc_dndr(LWL)
+        cube.s0 = s0_dev
+        rf = cube.solve()
+        sh = rtm.Shadowgraphy(rf)
+        sh.solve()
+        sh.histogram(to_host=False)
+        H = ttd.allreduce_histograms([sh.H_dev])[0]
+        return H, cube._steps_dev
+
+    def timed(fn, c, warmup, steps, sampler=None):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        c._trace_events = []                    # CUDA events around every trace launch from here on
+        if sampler:
+            sampler.start()
+        ev[0].record()
+        counters, last = [], None
+        for _ in range(steps):
+            last = fn()
+            counters.append(last[1])
+        ev[1].record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            torch.distributed.barrier()
+        ms = ev[0].elapsed_time(ev[1])
+        trace_ms[:] = c.trace_ms()
+        c._trace_events = None
+        ms = ttd.allreduce_scalar(float(ms), "max", device=dev)
+        tot_steps = ttd.allreduce_scalar(int(sum(int(t.item()) for t in counters)), "sum", device=dev)
+        return ms, tot_steps, last, clocks
+
+    ms, tot_steps, last, clocks = timed(step_device, cube, args.warmup, args.steps, ClockSampler(local))
+    kernel_ms = float(np.mean(trace_ms)) if trace_ms else float("nan")
+    steps_per_launch = tot_steps / (args.steps * world)
+    value = tot_steps / (ms * 1e-3)
+    H_dev = last[0]
+    rays_per_s = rays * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: public API, host pinned buffers in, histogram + counter out --------------------------
+    e2e = None
+    if not args.no_e2e:
+        ne_host = torch.empty((M, M, M), dtype=torch.float32, pin_memory=True)
+        ne_host.copy_(ne)
+        s0_host = torch.empty((6, rays), dtype=torch.float64, pin_memory=True)
+        s0_host.copy_(s0_dev.torch)
+        torch.cuda.synchronize()
+        cube2 = make_cube()
+        ne_np, s0_np = ne_host.numpy(), s0_host.numpy()
+
+        def step_e2e():
+            cube2.external_ne(ne_np)                # host numpy -> H2D inside calc_dndr
+            cube2.calc_dndr(LWL)
+            cube2.s0 = s0_np                        # host numpy -> H2D inside solve
+            rf = cube2.solve()
+            sh = rtm.Shadowgraphy(rf)
+            sh.solve()
+            sh.histogram()                          # D2H of the histogram inside
+            H = ttd.allreduce_histograms([sh.H_dev])[0]
+            _ = cube2.ray_steps                     # D2H of the counter
+            return H, cube2._steps_dev
+
+        ms2, tot2, _, _ = timed(step_e2e, cube2, 1, args.steps)
+        e2e = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
+               "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),
+               "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
+        del ne_host, s0_host
+
+    # ---- roofline of the dominant kernel (trace) ---------------------------------------------------
+    peak, peak_src = measured_hbm_peak()
+    bytes_per_step = ALGO_BYTES_PER_RAY_STEP * (2 if dtype == "float64" else 1)
+    achieved = steps_per_launch * bytes_per_step / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "trace_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kernel_ms, "ray_steps_per_launch": steps_per_launch,
+                "algorithmic_bytes_per_ray_step": bytes_per_step,
+                "note": "algorithmic bytes (4 stages x 8 corners x 16 B); corners shared by neighbouring rays are "
+                        "served by L1/L2, so DRAM traffic is far lower -- see profiles/"}
+
+    # ---- CPU baseline on a bounded sample of the same cube (rank 0, N = 1 only) ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            # a fresh process (no CUDA context to fork) runs the CPU path on the very same cube
+            path = f"/tmp/tt_ne_{os.getpid()}.npy"
+            np.save(path, ne.cpu().numpy())
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", wl,
+                                  "--cube-file", path, "--steps", "1", "--warmup", "0", "--cpu-rays",
+                                  str(args.cpu_rays)], capture_output=True, text=True, timeout=1500)
+            os.remove(path)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:      # reported, never silently dropped
+            cpu = {"value": None, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {type(e).__name__}: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": "ray-steps/s", "value": value, "unit": "ray-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
+            "rays_per_s": rays_per_s,
+            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_gpu": rays, "steps_per_cell": args.steps_per_cell,
+                       "beam_size_m": BEAM_SIZE, "divergence_rad": DIVERGENCE, "detector": "Shadowgraphy bin_scale=10",
+                       "parallelism": f"rays sharded x{world}, cube replicated (NCCL broadcast), histogram all-reduce",
+                       "l2": "inputs larger than L2 (gradient grid %.2f GB, rays %.2f GB)" % (
+                           M**3 * (16 if dtype == "float32" else 32) / 1e9, rays * 48 / 1e9),
+                       "cube_setup_s": t_cube, "kernel_variant": args.variant},
+            "e2e": e2e, "gpu_launches": 4 * args.steps,
+            "gpu_launches_note": "per step: calc_dndr, morton_key, trace, optics_hist (+ CUB radix-sort passes)",
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "histogram_sum": int(H_dev.sum().item()),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rays", type=int, default=0, help="override rays per GPU")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--steps-per-cell", type=int, default=1)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cpu-rays", type=int, default=2000, help="rays per host process in the CPU baseline sample")
+    ap.add_argument("--cube-file", default="", help="(reference arm) .npy ne cube to trace instead of a host GRF")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args, args.workload)
+    else:
+        run_gpu_arm(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

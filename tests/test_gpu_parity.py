@@ -169,7 +169,10 @@ def test_trace_grf_convergence_and_modes(tt, golden):
             assert cube.ray_steps == 32 * 4 * g["s0"].shape[1]
     print("grf33 fp64 (pos m, angle/rms) by steps_per_cell:", errs)
     assert errs[8][0] <= 1e-5 * 4e-3 and errs[8][1] <= 1e-5
-    assert errs[8][1] < errs[2][1] / 4          # at least ~2nd order
+    # ~2nd order (x4 per halving) until the oracle's own accuracy (rtol 1e-10: ~1.6e-6 of the rms
+    # angle, SURVEY section 6 self-convergence table) is reached
+    assert errs[2][1] < errs[1][1] / 3 and errs[2][0] < errs[1][0] / 3
+    assert errs[4][1] <= 3e-6 and errs[8][1] <= 3e-6
     cube = pt.ElectronCube(g["x"], g["x"], g["x"], dtype="float32", steps_per_cell=4, verbose=False)
     cube.external_ne(g["ne"])
     cube.calc_dndr()
@@ -226,9 +229,16 @@ def test_rays_outside_and_edge_cases(tt):
     rf = np.asarray(cube.solve(return_status=True))
     st = np.asarray(cube.status)
     assert st[0] & 8 and st[2] & 2 and st[3] & 1
-    np.testing.assert_allclose(rf[1], rf_ref[1], rtol=0, atol=2e-6)
-    np.testing.assert_allclose(rf[0], rf_ref[0], rtol=0, atol=2e-8)
-    np.testing.assert_allclose(np.asarray(cube.sf)[:3], sf_ref[:3], rtol=0, atol=5e-8)
+    # Ray 3 starts 3 mm in front of the cube.  scipy's adaptive RK45 sees a zero right-hand side
+    # there, grows its step tenfold per step and leaps over the whole cube (the oracle returns an
+    # undeflected ray) -- a solver artefact of the reference for rays launched outside the cube.
+    # The physical answer is the slab deflection of the other on-axis rays, which is what we give.
+    assert rf_ref[1, 3] == 0.0
+    assert rf[1, 3] == pytest.approx(rf[1, 5], rel=1e-9) and rf[0, 3] == pytest.approx(rf[0, 5], abs=1e-12)
+    keep = [0, 1, 2, 4, 5]
+    np.testing.assert_allclose(rf[1][keep], rf_ref[1][keep], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(rf[0][keep], rf_ref[0][keep], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(np.asarray(cube.sf)[:3, keep], sf_ref[:3, keep], rtol=0, atol=5e-8)
     # empty bundle
     cube.s0 = np.zeros((6, 0))
     assert np.asarray(cube.solve()).shape == (4, 0)
@@ -356,7 +366,7 @@ def test_histogram_edge_semantics(tt):
     vals = np.array([-9.0, 9.0, xe[17], np.nextafter(xe[17], -np.inf), 9.0000001, -9.0000001, np.nan, 0.0]) * 1e-3
     r = np.zeros((4, vals.size))
     r[0] = vals
-    r[2] = 0.0
+    r[2] = np.where(np.isnan(vals), np.nan, 0.0)      # rejected rays are NaN in every row (:78)
     d = rtm.Rays(r)
     d.rf = rtm.m_to_mm(r)
     d.histogram()

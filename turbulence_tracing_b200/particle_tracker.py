@@ -313,8 +313,16 @@ class ElectronCube:
         sf = torch.empty((6, Np), dtype=torch.float64, device="cuda") if self.keep_sf else None
         steps = torch.zeros(1, dtype=torch.int64, device="cuda")
         status = torch.empty(Np, dtype=torch.uint8, device="cuda") if return_status else None
+        events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
+        if events is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0), Np, _lib.ptr(perm), _lib.ptr(rf),
                                 _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
+        if events is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            events.append((e0, e1))
         self._perm = perm
         if self.verbose:
             torch.cuda.current_stream().synchronize()
@@ -335,6 +343,11 @@ class ElectronCube:
     @ray_steps.setter
     def ray_steps(self, v):
         self._steps_dev = None
+
+    def trace_ms(self):
+        """Durations (ms) of the trace-kernel launches recorded since ``_trace_events = []`` was set;
+        call after a synchronize."""
+        return [a.elapsed_time(b) for a, b in (getattr(self, "_trace_events", None) or [])]
 
     def ray_at_exit(self):
         """rf from ``self.sf`` by linear back-projection to the plane axis = +extent (:333-380)."""

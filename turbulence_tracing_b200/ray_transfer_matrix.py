@@ -226,10 +226,11 @@ class Rays:
         if v is None:
             self._program = None
 
-    def histogram(self, bin_scale=10, pix_x=3448, pix_y=2574, clear_mem=False):
+    def histogram(self, bin_scale=10, pix_x=3448, pix_y=2574, clear_mem=False, to_host=True):
         """Bin detector-plane rays; defaults are for a KAF-8300 (:173-195).  Sets ``H``
         (pix_y//bin_scale, pix_x//bin_scale) float64 like numpy.histogram2d(...).T, ``xedges``,
-        ``yedges``; ``H_dev`` keeps the integer counts on the device (for NCCL all-reduce)."""
+        ``yedges``; ``H_dev`` keeps the integer counts on the device (for NCCL all-reduce).
+        ``to_host=False`` skips the device->host copy of H (multi-GPU drivers reduce H_dev first)."""
         torch = _lib.torch_cuda()
         nbx, nby = pix_x // bin_scale, pix_y // bin_scale
         # numpy.histogramdd builds its edges with linspace(range_min, range_max, bins + 1)
@@ -245,7 +246,7 @@ class Rays:
         else:
             raise AttributeError("no rays to bin: call solve() first")
         self.H_dev = H
-        self.H = H.double().cpu().numpy()
+        self.H = H.double().cpu().numpy() if to_host else None
         if clear_mem:
             self.clear_rays()
 
