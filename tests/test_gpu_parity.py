@@ -184,6 +184,32 @@ def test_trace_grf_convergence_and_modes(tt, golden):
     assert pos <= 1e-3 * PIXEL_M
 
 
+@pytest.mark.parametrize("dtype,spc", [("float64", 1), ("float64", 3), ("float32", 1), ("float32", 2)])
+def test_cached_kernel_equals_gather_kernel(tt, golden, dtype, spc):
+    """variant 0 (cell cached in registers, 4 loads/step) and variant 1 (8-corner gather at every
+    stage) integrate the same field with the same scheme: they may differ by rounding only."""
+    g = golden("trace_grf33")
+    pt = tt.particle_tracker
+    out = {}
+    for variant in (0, 1):
+        cube = pt.ElectronCube(g["x"], g["x"], g["x"], dtype=dtype, steps_per_cell=spc, verbose=False)
+        cube.kernel_variant = variant
+        cube.external_ne(g["ne"])
+        cube.calc_dndr()
+        cube.init_beam(200_000, 5.2e-3, 2e-2, seed=5)       # wide, divergent beam: misses, side exits, cell changes
+        out[variant] = (np.asarray(cube.solve(return_status=True)), np.asarray(cube.status), cube.ray_steps,
+                        np.asarray(cube.sf))
+    (a, sa, na, fa), (b, sb, nb, fb) = out[0], out[1]
+    np.testing.assert_array_equal(sa & 11, sb & 11)
+    assert (sa & 8).sum() > 100 and (sa & 2).sum() > 100                              # the side-exit path is exercised
+    assert abs(na - nb) <= 4
+    tol = 2e-13 if dtype == "float64" else 2e-9              # metres
+    assert np.abs(a[0] - b[0]).max() <= tol and np.abs(a[2] - b[2]).max() <= tol
+    atol = 1e-11 if dtype == "float64" else 2e-6
+    assert np.abs(a[1] - b[1]).max() <= atol and np.abs(a[3] - b[3]).max() <= atol
+    np.testing.assert_allclose(fa[:3], fb[:3], rtol=0, atol=10 * tol)
+
+
 def test_trace_liner_over_critical(tt, golden):
     """ne > nc: ne/nc clipped at ne_max, rays deflected by up to 90 degrees (notebook cells 21-27).
     Rays with |angle| <= 0.5 rad must match; steep ones only have to come out finite."""

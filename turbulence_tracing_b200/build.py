@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(compile_one, srcs))
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-L" + cuda_lib, "-lcufft",
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-L" + cuda_lib, "-lcufft",
            "-Xlinker", "-rpath," + cuda_lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -213,7 +213,221 @@ __device__ __forceinline__ void clamp_in(int& i, T& f, int n) {
     if (i > n - 1 || (i == n - 1 && f > T(0))) { i = n - 1; f = T(0); }
 }
 
+
+// bookkeeping shared by the marching loops
 template <typename T>
+struct March {
+    int& st;
+    unsigned& steps;
+    bool& alive;
+    bool& general;
+};
+
+// Plane marching with a full 8-corner gather at every stage (the straightforward kernel; also
+// used for the partial first cell of rays that enter through a side face and for side exits).
+// Marches from (r.iw, r.fw) to the far face, or only to the next integer plane (until_plane).
+template <typename T>
+__device__ __noinline__ void march_generic(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+                                           Ray<T>& r, March<T>& m, T s_left0, int spc, bool until_plane) {
+    const T hsub = T(1) / (T)spc;
+    int k = r.iw;
+    T fw = r.fw;
+    int j = (int)(fw * (T)spc);          // sub-plane interval index containing fw
+    while (k < C.nw - 1) {
+        T fwb = (j + 1 == spc) ? T(1) : (T)(j + 1) * hsub;
+        T h = fwb - fw;
+        Ray<T> old = r;
+        bool ok = zstep<T>(grid, C, r, k, fw, h);
+        ++m.steps;
+        bool bad = !ok || !(r.dw > T(TT_MARCH_MIN_DW)) || !(r.s <= s_left0);
+        if (bad) {          // hand the step to the general integrator from the old state
+            r = old; r.iw = k; r.fw = fw; --m.steps;
+            m.general = true;
+            return;
+        }
+        T lu = leave_fraction(old.iu, old.fu, r.fu, C.nu);
+        T lv = leave_fraction(old.iv, old.fv, r.fv, C.nv);
+        T lam = fmin(lu, lv);
+        if (lam <= T(1)) {   // side exit: re-step to the face, freeze
+            r = old;
+            lam = lam < T(0) ? T(0) : lam;
+            zstep<T>(grid, C, r, k, fw, lam * h);
+            r.iw = k; r.fw = fw + lam * h;
+            clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv);
+            m.st |= TT_RAY_EXIT_SIDE;
+            m.alive = false;
+            return;
+        }
+        renorm(r.iu, r.fu); renorm(r.iv, r.fv);
+        fw = fwb;
+        if (++j == spc) {
+            j = 0; ++k; fw = T(0);
+            if (until_plane) { r.iw = k; r.fw = T(0); return; }
+        }
+    }
+    r.iw = C.nw - 1; r.fw = T(0);
+    m.st |= TT_RAY_EXIT_FACE;
+    m.alive = false;
+}
+
+// ---- the fast path: plane marching with the ray's cell cached in registers ----------------------
+// A ray moves ~1e-2 cells sideways per plane, so consecutive steps (and all four stages of a step)
+// almost always sit in the same (u, v) cell column.  The 2 x 4 corners of the current cell are kept
+// in registers as bilinear coefficient sets  g(tu, tv) = A + tu B + tv (C + tu D)  per plane (3 FMA
+// per component), the next plane's 4 corners are prefetched while the step is computed, and a step
+// then issues 4 instead of 32 corner loads.  A stage that leaves the cell gathers its 8 corners
+// from memory (same arithmetic as march_generic); a ray that changes cell reloads its cache.
+template <typename T>
+struct PlaneC {
+    T ax, bx, cx, dx, ay, by, cy, dy, az, bz, cz, dz;
+};
+template <typename T>
+__device__ __forceinline__ void make_plane(PlaneC<T>& P, const typename GridT<T>::V4& c00,
+                                           const typename GridT<T>::V4& c10, const typename GridT<T>::V4& c01,
+                                           const typename GridT<T>::V4& c11) {
+    P.ax = c00.x; P.bx = c10.x - c00.x; P.cx = c01.x - c00.x; P.dx = (c11.x - c01.x) - P.bx;
+    P.ay = c00.y; P.by = c10.y - c00.y; P.cy = c01.y - c00.y; P.dy = (c11.y - c01.y) - P.by;
+    P.az = c00.z; P.bz = c10.z - c00.z; P.cz = c01.z - c00.z; P.dz = (c11.z - c01.z) - P.bz;
+}
+template <typename T>
+__device__ __forceinline__ void load_plane(PlaneC<T>& P, const typename GridT<T>::V4* __restrict__ p, int nu) {
+    typedef typename GridT<T>::V4 V4;
+    V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+    make_plane<T>(P, c00, c10, c01, c11);
+}
+template <typename T>
+__device__ __forceinline__ G3<T> eval_plane(const PlaneC<T>& P, T tu, T tv) {
+    G3<T> g;
+    g.x = tfma(tv, tfma(tu, P.dx, P.cx), tfma(tu, P.bx, P.ax));
+    g.y = tfma(tv, tfma(tu, P.dy, P.cy), tfma(tu, P.by, P.ay));
+    g.z = tfma(tv, tfma(tu, P.dz, P.cz), tfma(tu, P.bz, P.az));
+    return g;
+}
+template <typename T> __device__ __forceinline__ T trcp(T x);
+template <> __device__ __forceinline__ float trcp<float>(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);        // one Newton step: ~1 ulp
+}
+template <> __device__ __forceinline__ double trcp<double>(double x) { return 1.0 / x; }
+
+template <typename T, bool SPC1>
+__device__ __forceinline__ void march_cached(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+                                             Ray<T>& r, March<T>& m, T s_left0, int spc, bool track_s) {
+    typedef typename GridT<T>::V4 V4;
+    int k = r.iw;                                   // r.fw == 0: the ray sits on plane k
+    if (k >= C.nw - 1) { r.iw = C.nw - 1; r.fw = T(0); m.st |= TT_RAY_EXIT_FACE; m.alive = false; return; }
+    int cu, cv; T tu, tv;
+    cell_of(r.iu, r.fu, C.nu, cu, tu); cell_of(r.iv, r.fv, C.nv, cv, tv);
+    T du = r.du, dv = r.dv, dw = r.dw, s = r.s;
+    const V4* p = grid + ((size_t)k * C.plane + (size_t)cv * C.nu + cu);
+    PlaneC<T> P0, P1;
+    load_plane<T>(P0, p, C.nu);
+    load_plane<T>(P1, p + C.plane, C.nu);
+    const T hsub = SPC1 ? T(1) : T(1) / (T)spc;
+
+    // field at stage position (su, sv) of the current cell, w-fraction fwq (wsel 0: plane k, 1: plane
+    // k+1, 2: general); outside the cached cell: full gather
+    auto field = [&](T su, T sv, T fwq, int wsel) -> G3<T> {
+        if (su >= T(0) && su <= T(1) && sv >= T(0) && sv <= T(1)) {
+            if (wsel == 0) return eval_plane<T>(P0, su, sv);
+            if (wsel == 1) return eval_plane<T>(P1, su, sv);
+            G3<T> a = eval_plane<T>(P0, su, sv), b = eval_plane<T>(P1, su, sv), g;
+            g.x = tfma(fwq, b.x - a.x, a.x); g.y = tfma(fwq, b.y - a.y, a.y); g.z = tfma(fwq, b.z - a.z, a.z);
+            return g;
+        }
+        int c1, c2; T t1, t2;
+        cell_of(cu, su, C.nu, c1, t1); cell_of(cv, sv, C.nv, c2, t2);
+        return trilinear<T>(grid, C.nu, C.plane, c1, c2, k, t1, t2, fwq);
+    };
+
+    while (true) {
+        // prefetch the 4 corners of plane k+2 for this cell; consumed when the step is done
+        const bool has_next = k + 2 <= C.nw - 1;
+        V4 n00, n10, n01, n11;
+        if (has_next) {
+            const V4* q = p + 2 * C.plane;
+            n00 = GridT<T>::ld(q); n10 = GridT<T>::ld(q + 1); n01 = GridT<T>::ld(q + C.nu); n11 = GridT<T>::ld(q + C.nu + 1);
+        }
+        for (int j = 0; j < (SPC1 ? 1 : spc); ++j) {
+            const T fwa = SPC1 ? T(0) : (T)j * hsub;
+            const T fwb = SPC1 ? T(1) : ((j + 1 == spc) ? T(1) : (T)(j + 1) * hsub);
+            const T h = fwb - fwa, half = T(0.5) * h;
+            // ---- RK4 in W -----------------------------------------------------------------------
+            G3<T> g = field(tu, tv, fwa, SPC1 ? 0 : 2);
+            T q = trcp<T>(dw), hq = C.hw * q;
+            bool ok = dw > T(0);
+            const T aU = C.ru * du * q, aV = C.rv * dv * q, adu = g.x * hq, adv = g.y * hq, adw = g.z * hq, as = hq;
+            T du2 = tfma(half, adu, du), dv2 = tfma(half, adv, dv), dw2 = tfma(half, adw, dw);
+            g = field(tfma(half, aU, tu), tfma(half, aV, tv), fwa + half, 2);
+            q = trcp<T>(dw2); hq = C.hw * q; ok = ok && dw2 > T(0);
+            const T bU = C.ru * du2 * q, bV = C.rv * dv2 * q, bdu = g.x * hq, bdv = g.y * hq, bdw = g.z * hq, bs = hq;
+            du2 = tfma(half, bdu, du); dv2 = tfma(half, bdv, dv); dw2 = tfma(half, bdw, dw);
+            g = field(tfma(half, bU, tu), tfma(half, bV, tv), fwa + half, 2);
+            q = trcp<T>(dw2); hq = C.hw * q; ok = ok && dw2 > T(0);
+            const T cU = C.ru * du2 * q, cV = C.rv * dv2 * q, cdu = g.x * hq, cdv = g.y * hq, cdw = g.z * hq, cs = hq;
+            du2 = tfma(h, cdu, du); dv2 = tfma(h, cdv, dv); dw2 = tfma(h, cdw, dw);
+            g = field(tfma(h, cU, tu), tfma(h, cV, tv), fwb, SPC1 ? 1 : 2);
+            q = trcp<T>(dw2); hq = C.hw * q; ok = ok && dw2 > T(0);
+            const T eU = C.ru * du2 * q, eV = C.rv * dv2 * q, edu = g.x * hq, edv = g.y * hq, edw = g.z * hq, es = hq;
+            const T h6 = h * T(1.0 / 6.0);
+            const T tu_n = tfma(h6, aU + T(2) * (bU + cU) + eU, tu);
+            const T tv_n = tfma(h6, aV + T(2) * (bV + cV) + eV, tv);
+            const T du_n = tfma(h6, adu + T(2) * (bdu + cdu) + edu, du);
+            const T dv_n = tfma(h6, adv + T(2) * (bdv + cdv) + edv, dv);
+            const T dw_n = tfma(h6, adw + T(2) * (bdw + cdw) + edw, dw);
+            const T s_n = track_s ? tfma(h6, as + T(2) * (bs + cs) + es, s) : s;
+            ++m.steps;
+            if (!ok || !(dw_n > T(TT_MARCH_MIN_DW)) || !(s_n <= s_left0)) {
+                // steep / turning ray: the general integrator redoes this step from the old state
+                r.iu = cu; r.fu = tu; r.iv = cv; r.fv = tv; r.iw = k; r.fw = fwa;
+                r.du = du; r.dv = dv; r.dw = dw; r.s = s;
+                --m.steps;
+                m.general = true;
+                return;
+            }
+            if (!(tu_n >= T(0) && tu_n <= T(1) && tv_n >= T(0) && tv_n <= T(1))) {
+                // left the cached cell: side exit of the cube, or a new cell whose corners are reloaded
+                T lam = fmin(leave_fraction(cu, tu, tu_n, C.nu), leave_fraction(cv, tv, tv_n, C.nv));
+                if (lam <= T(1)) {
+                    r.iu = cu; r.fu = tu; r.iv = cv; r.fv = tv; r.iw = k; r.fw = fwa;
+                    r.du = du; r.dv = dv; r.dw = dw; r.s = s;
+                    lam = lam < T(0) ? T(0) : lam;
+                    zstep<T>(grid, C, r, k, fwa, lam * h);
+                    r.fw = fwa + lam * h;
+                    clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv);
+                    m.st |= TT_RAY_EXIT_SIDE;
+                    m.alive = false;
+                    return;
+                }
+                int c1, c2; T t1, t2;
+                cell_of(cu, tu_n, C.nu, c1, t1); cell_of(cv, tv_n, C.nv, c2, t2);
+                cu = c1; cv = c2; tu = t1; tv = t2;
+                p = grid + ((size_t)k * C.plane + (size_t)cv * C.nu + cu);
+                if (!SPC1 && j + 1 < spc) load_plane<T>(P0, p, C.nu);
+                load_plane<T>(P1, p + C.plane, C.nu);
+                if (has_next) {
+                    const V4* q2 = p + 2 * C.plane;
+                    n00 = GridT<T>::ld(q2); n10 = GridT<T>::ld(q2 + 1); n01 = GridT<T>::ld(q2 + C.nu); n11 = GridT<T>::ld(q2 + C.nu + 1);
+                }
+            } else {
+                tu = tu_n; tv = tv_n;
+            }
+            du = du_n; dv = dv_n; dw = dw_n; s = s_n;
+        }
+        ++k;
+        if (k >= C.nw - 1) break;
+        p += C.plane;
+        P0 = P1;
+        make_plane<T>(P1, n00, n10, n01, n11);
+    }
+    r.iu = cu; r.fu = tu; r.iv = cv; r.fv = tv; r.iw = C.nw - 1; r.fw = T(0);
+    r.du = du; r.dv = dv; r.dw = dw; r.s = s;
+    m.st |= TT_RAY_EXIT_FACE;
+    m.alive = false;
+}
+
+template <typename T, int VARIANT>
 __global__ void __launch_bounds__(128) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
                                                     const double* __restrict__ s0,
                                                     const uint32_t* __restrict__ perm,
@@ -290,43 +504,19 @@ __global__ void __launch_bounds__(128) trace_kernel(const typename GridT<T>::V4*
 
         // ---- plane marching ---------------------------------------------------------------------
         if (alive && !(r.dw > T(TT_MARCH_MIN_DW))) general = true;
+        // rays that could run into the path-time cap c*T while marching are integrated by the general
+        // loop, which stops exactly at the cap (never the case for the reference's symmetric cubes)
+        if (alive && !general && (T)(C.nw - 1 - r.iw) * C.hw > T(TT_MARCH_MIN_DW) * s_left0) general = true;
         if (alive && !general) {
-            int k = r.iw;
-            T fw = r.fw;
-            int j = (int)(fw * (T)A.spc);          // sub-plane interval index containing fw
-            while (k < C.nw - 1) {
-                T fwb = (j + 1 == A.spc) ? T(1) : (T)(j + 1) * hsub;
-                T h = fwb - fw;
-                Ray<T> old = r;
-                bool ok = zstep<T>(grid, C, r, k, fw, h);
-                ++steps;
-                bool bad = !ok || !(r.dw > T(TT_MARCH_MIN_DW)) || !(r.s <= s_left0);
-                if (bad) {          // hand the step to the general integrator from the old state
-                    r = old; r.iw = k; r.fw = fw; --steps;
-                    general = true;
-                    break;
+            March<T> m{st, steps, alive, general};
+            if (VARIANT == 1) {
+                march_generic<T>(grid, C, r, m, s_left0, A.spc, false);
+            } else {
+                if (r.fw != T(0)) march_generic<T>(grid, C, r, m, s_left0, A.spc, true);   // entry through a side face
+                if (alive && !general) {
+                    if (A.spc == 1) march_cached<T, true>(grid, C, r, m, s_left0, 1, sf != nullptr);
+                    else march_cached<T, false>(grid, C, r, m, s_left0, A.spc, sf != nullptr);
                 }
-                T lu = leave_fraction(old.iu, old.fu, r.fu, C.nu);
-                T lv = leave_fraction(old.iv, old.fv, r.fv, C.nv);
-                T lam = fmin(lu, lv);
-                if (lam <= T(1)) {   // side exit: re-step to the face, freeze
-                    r = old;
-                    lam = lam < T(0) ? T(0) : lam;
-                    zstep<T>(grid, C, r, k, fw, lam * h);
-                    r.iw = k; r.fw = fw + lam * h;
-                    clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv);
-                    st |= TT_RAY_EXIT_SIDE;
-                    alive = false;
-                    break;
-                }
-                renorm(r.iu, r.fu); renorm(r.iv, r.fv);
-                fw = fwb;
-                if (++j == A.spc) { j = 0; ++k; fw = T(0); }
-            }
-            if (alive && !general) {
-                r.iw = C.nw - 1; r.fw = T(0);
-                st |= TT_RAY_EXIT_FACE;
-                alive = false;
             }
         }
         // ---- general arc-length integrator (steep / backward / time-capped rays) ----------------
@@ -467,12 +657,13 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     const long blocks = (np + block - 1) / block;
     TT_REQUIRE(blocks < (1L << 31), "tt_trace: too many rays for one launch");
     cudaStream_t s = (cudaStream_t)stream;
-    if (p->dtype == TT_F32)
-        trace_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
-                                                               sf_dev, ray_steps_dev, status_dev, A);
-    else
-        trace_kernel<double><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev,
-                                                                sf_dev, ray_steps_dev, status_dev, A);
+    TT_REQUIRE(p->variant == 0 || p->variant == 1, "tt_trace: unknown kernel variant %d", p->variant);
+#define TT_LAUNCH(TYPE, V4T, VAR)                                                                                 \
+    trace_kernel<TYPE, VAR><<<(unsigned)blocks, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev,    \
+                                                                sf_dev, ray_steps_dev, status_dev, A)
+    if (p->dtype == TT_F32) { if (p->variant == 1) TT_LAUNCH(float, float4, 1); else TT_LAUNCH(float, float4, 0); }
+    else { if (p->variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
+#undef TT_LAUNCH
     return launch_check("trace_kernel");
 }
 

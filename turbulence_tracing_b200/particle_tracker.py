@@ -288,6 +288,12 @@ class ElectronCube:
         if s0.dim() != 2 or s0.shape[0] != 6:
             raise ValueError("s0 must have shape (6, Np)")
         Np = s0.shape[1]
+        if Np == 0:                                   # empty bundle: nothing to launch
+            self.rf = DeviceArray(torch.empty((4, 0), dtype=torch.float64, device="cuda"))
+            self.sf = DeviceArray(torch.empty((6, 0), dtype=torch.float64, device="cuda")) if self.keep_sf else None
+            self.status = DeviceArray(torch.empty(0, dtype=torch.uint8, device="cuda")) if return_status else None
+            self._steps_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+            return self.rf
         stream = _lib.stream_ptr()
         start = time()
         perm = None
