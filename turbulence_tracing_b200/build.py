@@ -46,12 +46,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("TT_NVCC_EXTRA", "").split()      # tuning experiments, e.g. -DTT_TRACE_MIN_BLOCKS=4
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if not force and _newer(obj, [src] + headers):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

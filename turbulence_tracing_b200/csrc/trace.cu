@@ -25,6 +25,9 @@ namespace tt {
 
 static constexpr double kC = 299792458.0;      // scipy.constants.c (particle_tracker.py:119)
 #define TT_MARCH_MIN_DW 0.75
+#ifndef TT_TRACE_MIN_BLOCKS
+#define TT_TRACE_MIN_BLOCKS 3      // CTAs of 128 threads per SM the register allocation aims for
+#endif
 
 struct TraceArgs {
     int n[3];        // nu, nv, nw
@@ -428,7 +431,7 @@ __device__ __forceinline__ void march_cached(const typename GridT<T>::V4* __rest
 }
 
 template <typename T, int VARIANT>
-__global__ void __launch_bounds__(128) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
+__global__ void __launch_bounds__(128, TT_TRACE_MIN_BLOCKS) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
                                                     const double* __restrict__ s0,
                                                     const uint32_t* __restrict__ perm,
                                                     double* __restrict__ rf, double* __restrict__ sf,
