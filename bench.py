@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--steps-per-cell", type=int, default=1)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--cpu-rays", type=int, default=10000, help="rays per host process in the CPU baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=3000, help="rays per host process in the CPU baseline sample")
     ap.add_argument("--cube-file", default="", help="(reference arm) .npy ne cube to trace instead of a host GRF")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -104,7 +104,8 @@ typedef struct tt_trace_params {
     double s_max;           /* c*T                                           */
     int steps_per_cell;     /* >= 1                                          */
     int dtype;              /* TT_F32 or TT_F64: grid element type and state arithmetic */
-    int variant;            /* 0 = default kernel; others select experimental kernels  */
+    int variant;            /* 0 = auto (event marching if status_dev is given, else cell cache);
+                               1 = 8-corner gather per stage; 2 = cell cache; 3 = event marching */
 } tt_trace_params;
 
 int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_dev, long np,
@@ -156,6 +157,13 @@ int tt_grf_workspace(int N, int dtype, size_t* bytes);
 int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev,
              const double* Wi_dev, uint64_t seed, void* out_dev, void* workspace_dev,
              size_t workspace_bytes, tt_stream_t stream);
+
+/* 1-D / 2-D / 3-D variants (gaussian1D_FFT :388-434, gaussian2D_FFT :436-486): ndim = 1, 2, 3; arrays
+ * have shape (2N+1,)*ndim; the table needs ndim*N^2+1 entries.                                    */
+int tt_grf_nd_workspace(int ndim, int N, int dtype, size_t* bytes);
+int tt_grf_nd(int ndim, int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev,
+              const double* Wi_dev, uint64_t seed, void* out_dev, void* workspace_dev,
+              size_t workspace_bytes, tt_stream_t stream);
 
 /* ---- host-buffer convenience entry point (what a ctypes binding inside the reference calls) --
  * Whole path for one bundle of rays with HOST arrays: ne (C order, double) -> gradient grid ->

@@ -62,6 +62,8 @@ PROTOTYPES = {
     "tt_optics_hist_perm": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_grf_workspace": (_i, [_i, _i, C.POINTER(_sz)]),
     "tt_grf3d": (_i, [_i, _i, _vp, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
+    "tt_grf_nd_workspace": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "tt_grf_nd": (_i, [_i, _i, _i, _vp, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
     "tt_solve_host": (_i, [_vp, C.POINTER(_I3), C.POINTER(_D3), C.POINTER(_D3), _i, _d, _d, _d, _i, _i, _vp, _l,
                            _vp, _vp, C.POINTER(C.c_ulonglong)]),
 }

@@ -62,7 +62,7 @@ extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const do
     size_t sort_bytes = 0;
     int rc = tt_sort_rays_workspace(np, &sort_bytes);
     if (rc) return rc;
-    DevBuf ne, grid, s0, rf, sf, perm, ws, cnt;
+    DevBuf ne, grid, s0, rf, sf, perm, ws, cnt, status;
     TT_CUDA(ne.alloc(nvox * sizeof(double)));
     TT_CUDA(grid.alloc(nvox * (dtype == TT_F32 ? 16 : 32)));
     TT_CUDA(s0.alloc((size_t)np * 6 * sizeof(double)));
@@ -71,6 +71,7 @@ extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const do
     TT_CUDA(perm.alloc((size_t)np * sizeof(uint32_t)));
     TT_CUDA(ws.alloc(sort_bytes));
     TT_CUDA(cnt.alloc(sizeof(unsigned long long)));
+    TT_CUDA(status.alloc((size_t)np));
     cudaStream_t s = 0;
     TT_CUDA(cudaMemcpyAsync(ne.p, ne_host, nvox * sizeof(double), cudaMemcpyHostToDevice, s));
     TT_CUDA(cudaMemcpyAsync(s0.p, s0_host, (size_t)np * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -93,7 +94,7 @@ extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const do
     p.steps_per_cell = steps_per_cell;
     p.dtype = dtype;
     rc = tt_trace(&p, grid.p, (const double*)s0.p, np, (const uint32_t*)perm.p, (double*)rf.p, (double*)sf.p,
-                  (unsigned long long*)cnt.p, nullptr, s);
+                  (unsigned long long*)cnt.p, (uint8_t*)status.p, s);
     if (rc) return rc;
     TT_CUDA(cudaMemcpyAsync(rf_host, rf.p, (size_t)np * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (sf_host) TT_CUDA(cudaMemcpyAsync(sf_host, sf.p, (size_t)np * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));

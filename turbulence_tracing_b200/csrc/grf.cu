@@ -25,22 +25,24 @@ __device__ __forceinline__ void philox_normals(uint64_t idx, uint64_t seed, doub
 
 // one thread per element of the half spectrum (a, b, c), c = 0..N
 template <typename T>
-__global__ void __launch_bounds__(256) grf_spectrum_kernel(int N, const double* __restrict__ lut,
+__global__ void __launch_bounds__(256) grf_spectrum_kernel(int N, int Ma, int Mb, const double* __restrict__ lut,
                                                            const double* __restrict__ Wr,
                                                            const double* __restrict__ Wi, uint64_t seed,
                                                            double norm, typename Cplx<T>::type* __restrict__ F) {
+    // Ma, Mb: extent of the two leading axes (M for a 3-D field; 1 for the axes a 1-D / 2-D field lacks)
     const int M = 2 * N + 1, Nh = N + 1;
-    const size_t total = (size_t)M * M * Nh;
+    const size_t total = (size_t)Ma * Mb * Nh;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i % Nh);
-    const int b = (int)((i / Nh) % M);
-    const int a = (int)(i / ((size_t)Nh * M));
+    const int b = (int)((i / Nh) % Mb);
+    const int a = (int)(i / ((size_t)Nh * Mb));
+    const int Na = Ma == 1 ? 0 : N, Nb = Mb == 1 ? 0 : N;
     // signed frequencies of FFT-order indices
-    const int fa = a <= N ? a : a - M, fb = b <= N ? b : b - M, fc = c;
-    // index of +k and of -k in the fftshift-ed cubes Wr, Wi (:520-526)
-    const size_t jp = ((size_t)(N + fa) * M + (N + fb)) * M + (N + fc);
-    const size_t jm = ((size_t)(N - fa) * M + (N - fb)) * M + (N - fc);
+    const int fa = a <= Na ? a : a - Ma, fb = b <= Nb ? b : b - Mb, fc = c;
+    // index of +k and of -k in the fftshift-ed arrays Wr, Wi (:520-526)
+    const size_t jp = ((size_t)(Na + fa) * Mb + (Nb + fb)) * M + (N + fc);
+    const size_t jm = ((size_t)(Na - fa) * Mb + (Nb - fb)) * M + (N - fc);
     double wrp, wip, wrm, wim;
     if (Wr) {
         wrp = Wr[jp]; wrm = Wr[jm]; wip = Wi[jp]; wim = Wi[jm];
@@ -70,53 +72,64 @@ static int cufft_fail(cufftResult r, const char* what) {
 
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static int plan_size(int N, int dtype, size_t* spectrum_bytes, size_t* work_bytes) {
+static cufftResult make_plan(cufftHandle plan, int ndim, int M, int dtype, size_t* work_bytes) {
+    const cufftType t = dtype == TT_F32 ? CUFFT_C2R : CUFFT_Z2D;
+    if (ndim == 1) return cufftMakePlan1d(plan, M, t, 1, work_bytes);
+    if (ndim == 2) return cufftMakePlan2d(plan, M, M, t, work_bytes);
+    return cufftMakePlan3d(plan, M, M, M, t, work_bytes);
+}
+
+static int plan_size(int ndim, int N, int dtype, size_t* spectrum_bytes, size_t* work_bytes) {
     const int M = 2 * N + 1;
-    *spectrum_bytes = align256((size_t)M * M * (N + 1) * (dtype == TT_F32 ? 8 : 16));
+    size_t lead = ndim == 3 ? (size_t)M * M : (ndim == 2 ? (size_t)M : 1);
+    *spectrum_bytes = align256(lead * (N + 1) * (dtype == TT_F32 ? 8 : 16));
     cufftHandle plan;
     TT_FFT(cufftCreate(&plan));
     cufftResult r = cufftSetAutoAllocation(plan, 0);
-    if (r == CUFFT_SUCCESS) r = cufftMakePlan3d(plan, M, M, M, dtype == TT_F32 ? CUFFT_C2R : CUFFT_Z2D, work_bytes);
+    if (r == CUFFT_SUCCESS) r = make_plan(plan, ndim, M, dtype, work_bytes);
     cufftDestroy(plan);
-    if (r != CUFFT_SUCCESS) return cufft_fail(r, "cufftMakePlan3d(size query)");
+    if (r != CUFFT_SUCCESS) return cufft_fail(r, "cufftMakePlan(size query)");
     return TT_OK;
 }
 
 }  // namespace tt
 
-extern "C" int tt_grf_workspace(int N, int dtype, size_t* bytes) {
+extern "C" int tt_grf_nd_workspace(int ndim, int N, int dtype, size_t* bytes) {
     using namespace tt;
     TT_REQUIRE(bytes, "tt_grf_workspace: null pointer");
+    TT_REQUIRE(ndim >= 1 && ndim <= 3, "tt_grf: ndim must be 1, 2 or 3");
     TT_REQUIRE(N >= 1 && N <= 2047, "tt_grf: N out of range");
     TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_grf: dtype must be TT_F32 or TT_F64");
     size_t spec = 0, work = 0;
-    int rc = plan_size(N, dtype, &spec, &work);
+    int rc = plan_size(ndim, N, dtype, &spec, &work);
     if (rc) return rc;
     *bytes = spec + align256(work);
     return TT_OK;
 }
 
-extern "C" int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev, const double* Wi_dev,
-                        uint64_t seed, void* out_dev, void* workspace_dev, size_t workspace_bytes,
-                        tt_stream_t stream) {
+extern "C" int tt_grf_nd(int ndim, int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev,
+                         const double* Wi_dev, uint64_t seed, void* out_dev, void* workspace_dev,
+                         size_t workspace_bytes, tt_stream_t stream) {
     using namespace tt;
-    TT_REQUIRE(sqrtP_lut_dev && out_dev && workspace_dev, "tt_grf3d: null pointer");
-    TT_REQUIRE((Wr_dev == nullptr) == (Wi_dev == nullptr), "tt_grf3d: give both Wr and Wi or neither");
-    TT_REQUIRE(N >= 1 && N <= 2047, "tt_grf3d: N out of range");
-    TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_grf3d: dtype must be TT_F32 or TT_F64");
+    TT_REQUIRE(sqrtP_lut_dev && out_dev && workspace_dev, "tt_grf: null pointer");
+    TT_REQUIRE((Wr_dev == nullptr) == (Wi_dev == nullptr), "tt_grf: give both Wr and Wi or neither");
+    TT_REQUIRE(ndim >= 1 && ndim <= 3, "tt_grf: ndim must be 1, 2 or 3");
+    TT_REQUIRE(N >= 1 && N <= 2047, "tt_grf: N out of range");
+    TT_REQUIRE(dtype == TT_F32 || dtype == TT_F64, "tt_grf: dtype must be TT_F32 or TT_F64");
     size_t spec = 0, work = 0;
-    int rc = plan_size(N, dtype, &spec, &work);
+    int rc = plan_size(ndim, N, dtype, &spec, &work);
     if (rc) return rc;
-    TT_REQUIRE(workspace_bytes >= spec + align256(work), "tt_grf3d: workspace too small");
+    TT_REQUIRE(workspace_bytes >= spec + align256(work), "tt_grf: workspace too small");
     const int M = 2 * N + 1;
+    const int Ma = ndim == 3 ? M : 1, Mb = ndim >= 2 ? M : 1;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t total = (size_t)M * M * (N + 1);
+    const size_t total = (size_t)Ma * Mb * (N + 1);
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    const double norm = 1.0 / ((double)M * M * M);
+    const double norm = 1.0 / ((double)Ma * Mb * M);
     if (dtype == TT_F32)
-        grf_spectrum_kernel<float><<<blocks, 256, 0, s>>>(N, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (float2*)workspace_dev);
+        grf_spectrum_kernel<float><<<blocks, 256, 0, s>>>(N, Ma, Mb, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (float2*)workspace_dev);
     else
-        grf_spectrum_kernel<double><<<blocks, 256, 0, s>>>(N, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (double2*)workspace_dev);
+        grf_spectrum_kernel<double><<<blocks, 256, 0, s>>>(N, Ma, Mb, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, norm, (double2*)workspace_dev);
     rc = launch_check("grf_spectrum_kernel");
     if (rc) return rc;
 
@@ -124,7 +137,7 @@ extern "C" int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const dou
     TT_FFT(cufftCreate(&plan));
     size_t ws = 0;
     cufftResult r = cufftSetAutoAllocation(plan, 0);
-    if (r == CUFFT_SUCCESS) r = cufftMakePlan3d(plan, M, M, M, dtype == TT_F32 ? CUFFT_C2R : CUFFT_Z2D, &ws);
+    if (r == CUFFT_SUCCESS) r = make_plan(plan, ndim, M, dtype, &ws);
     if (r == CUFFT_SUCCESS) r = cufftSetWorkArea(plan, (char*)workspace_dev + spec);
     if (r == CUFFT_SUCCESS) r = cufftSetStream(plan, s);
     if (r == CUFFT_SUCCESS) {
@@ -134,4 +147,12 @@ extern "C" int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const dou
     cufftDestroy(plan);
     if (r != CUFFT_SUCCESS) return cufft_fail(r, "cuFFT C2R plan/exec");
     return TT_OK;
+}
+
+extern "C" int tt_grf_workspace(int N, int dtype, size_t* bytes) { return tt_grf_nd_workspace(3, N, dtype, bytes); }
+
+extern "C" int tt_grf3d(int N, int dtype, const double* sqrtP_lut_dev, const double* Wr_dev, const double* Wi_dev,
+                        uint64_t seed, void* out_dev, void* workspace_dev, size_t workspace_bytes,
+                        tt_stream_t stream) {
+    return tt_grf_nd(3, N, dtype, sqrtP_lut_dev, Wr_dev, Wi_dev, seed, out_dev, workspace_dev, workspace_bytes, stream);
 }

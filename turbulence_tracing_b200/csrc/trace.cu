@@ -25,6 +25,7 @@ namespace tt {
 
 static constexpr double kC = 299792458.0;      // scipy.constants.c (particle_tracker.py:119)
 #define TT_MARCH_MIN_DW 0.75
+#define TT_RAY_DEFERRED 0xFF       // internal status: ray left to the second-pass kernel
 #ifndef TT_TRACE_MIN_BLOCKS
 #define TT_TRACE_MIN_BLOCKS 3      // CTAs of 128 threads per SM the register allocation aims for
 #endif
@@ -431,16 +432,22 @@ __device__ __forceinline__ void march_cached(const typename GridT<T>::V4* __rest
 }
 
 template <typename T, int VARIANT>
-__global__ void __launch_bounds__(128, TT_TRACE_MIN_BLOCKS) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
                                                     const double* __restrict__ s0,
                                                     const uint32_t* __restrict__ perm,
                                                     double* __restrict__ rf, double* __restrict__ sf,
                                                     unsigned long long* __restrict__ ray_steps,
-                                                    uint8_t* __restrict__ status, TraceArgs A) {
+                                                    uint8_t* __restrict__ status, TraceArgs A, int only_flagged) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned steps = 0;
-    if (tid < A.np) {
-        const long ray = perm ? (long)perm[tid] : tid;
+    bool mine = tid < A.np;
+    long ray = 0;
+    if (mine) {
+        ray = perm ? (long)perm[tid] : tid;
+        // second pass behind trace_event_kernel: only the rays it handed over
+        if (only_flagged && status[ray] != TT_RAY_DEFERRED) mine = false;
+    }
+    if (mine) {
         double P[3], D[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -591,6 +598,226 @@ __global__ void __launch_bounds__(128, TT_TRACE_MIN_BLOCKS) trace_kernel(const t
     }
 }
 
+// ---- variant 3: event marching ---------------------------------------------------------------------
+// Every RK4 step lies inside ONE grid cell: a step ends on the next (sub-)plane of the probing axis
+// or, if the stage-1 slope predicts that the ray leaves its (u, v) cell column first, on that cell
+// face (chord fraction lambda of the remaining interval); the ray is then relabelled into the
+// neighbouring cell and continues.  Inside a cell the field is one trilinear polynomial
+//      g(tu, tv, fw) = (A + tu B + tv (C + tu D)) + fw (A' + tu B' + tv (C' + tu D'))
+// held in 24 registers per ray (7 FMA per component, no loads, no per-stage cell tests, no
+// divergence inside a step); the next plane's corners are prefetched one step ahead.  All lanes of a
+// warp stay converged in one loop (a lane with more cell crossings simply iterates a few more times),
+// and because no step straddles a kink of the piecewise-trilinear field the integrator keeps its 4th
+// order.  A predicted crossing lands within ~1e-4 cells of the face (chord vs arc); the ray keeps its
+// true position (fractions may be ~1e-4 outside [0, 1], where the polynomial is simply extrapolated).
+// Anything unusual -- launched outside the cube, steep or backward, side exit, possible time cap,
+// non-finite state -- is flagged TT_RAY_DEFERRED and integrated by the general kernel in a second
+// launch (none of the rays of a beam that fits the cube).
+#ifndef TT_EVENT_MIN_BLOCKS
+#define TT_EVENT_MIN_BLOCKS 5        // FP32: 95 registers, no spills -> 20 warps / SM
+#endif
+#ifndef TT_EVENT_MIN_BLOCKS_F64
+#define TT_EVENT_MIN_BLOCKS_F64 3
+#endif
+
+template <typename T>
+struct Tri {           // trilinear polynomial of one component in one cell
+    T a, b, c, d, a1, b1, c1, d1;
+};
+template <typename T>
+__device__ __forceinline__ T tri_eval(const Tri<T>& q, T tu, T tv, T fw) {
+    T lo = tfma(tv, tfma(tu, q.d, q.c), tfma(tu, q.b, q.a));
+    T hi = tfma(tv, tfma(tu, q.d1, q.c1), tfma(tu, q.b1, q.a1));
+    return tfma(fw, hi, lo);
+}
+// coefficients of plane 0 from its 4 corners; primed = plane 1 minus plane 0
+template <typename T>
+__device__ __forceinline__ void tri_set(Tri<T>& q, T c00, T c10, T c01, T c11, T e00, T e10, T e01, T e11) {
+    q.a = c00; q.b = c10 - c00; q.c = c01 - c00; q.d = (c11 - c01) - q.b;
+    T ea = e00, eb = e10 - e00, ec = e01 - e00, ed = (e11 - e01) - eb;
+    q.a1 = ea - q.a; q.b1 = eb - q.b; q.c1 = ec - q.c; q.d1 = ed - q.d;
+}
+// advance one plane: plane 1 becomes plane 0, (n00..n11) are the corners of the new plane 1
+template <typename T>
+__device__ __forceinline__ void tri_advance(Tri<T>& q, T n00, T n10, T n01, T n11) {
+    q.a += q.a1; q.b += q.b1; q.c += q.c1; q.d += q.d1;
+    T eb = n10 - n00;
+    q.a1 = n00 - q.a; q.b1 = eb - q.b; q.c1 = (n01 - n00) - q.c; q.d1 = ((n11 - n01) - eb) - q.d;
+}
+
+template <typename T, bool SPC1>
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? TT_EVENT_MIN_BLOCKS_F64 : TT_EVENT_MIN_BLOCKS)
+trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0,
+                   const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
+                   unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A) {
+    typedef typename GridT<T>::V4 V4;
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned steps = 0;
+    if (tid < A.np) {
+        const long ray = perm ? (long)perm[tid] : tid;
+        const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
+        const size_t plane = (size_t)nu * nv;
+        // ---- prologue ---------------------------------------------------------------------------
+        double X[3], D[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[k] = (s0[(size_t)A.fa[k] * A.np + ray] - A.o[k]) / A.h[k];
+            D[k] = s0[(size_t)(3 + A.fa[k]) * A.np + ray] * (1.0 / kC);
+        }
+        bool fast = X[0] >= 0.0 && X[0] <= (double)(nu - 1) && X[1] >= 0.0 && X[1] <= (double)(nv - 1) &&
+                    X[2] >= 0.0 && X[2] <= (double)(nw - 1) && D[2] > TT_MARCH_MIN_DW;
+        // the path-time cap must be out of reach while marching (d_w > 0.75 throughout)
+        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * A.s_max;
+        int cu = 0, cv = 0, k = 0;
+        T tu = T(0), tv = T(0), fw = T(0);
+        if (fast) {
+            double fl;
+            fl = fmin(floor(X[0]), (double)(nu - 2)); cu = (int)fl; tu = (T)(X[0] - fl);
+            fl = fmin(floor(X[1]), (double)(nv - 2)); cv = (int)fl; tv = (T)(X[1] - fl);
+            fl = floor(X[2]); k = (int)fl; fw = (T)(X[2] - fl);
+        }
+        T du = (T)D[0], dv = (T)D[1], dw = (T)D[2], s = T(0);
+        const T hw = (T)A.h[2], ru = (T)(A.h[2] / A.h[0]), rv = (T)(A.h[2] / A.h[1]);
+        const bool track_s = sf != nullptr;
+        const int spc = A.spc;
+        const T hsub = SPC1 ? T(1) : T(1) / (T)spc;
+        int j = SPC1 ? 0 : (int)(fw * (T)spc);       // current sub-plane interval of the w-cell
+
+        if (fast && k < nw - 1) {
+            const V4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
+            Tri<T> qx, qy, qz;
+            V4 n00, n10, n01, n11;                    // corners of plane k+2 (prefetch)
+            {
+                V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+                const V4* p1 = p + plane;
+                V4 e00 = GridT<T>::ld(p1), e10 = GridT<T>::ld(p1 + 1), e01 = GridT<T>::ld(p1 + nu), e11 = GridT<T>::ld(p1 + nu + 1);
+                tri_set<T>(qx, c00.x, c10.x, c01.x, c11.x, e00.x, e10.x, e01.x, e11.x);
+                tri_set<T>(qy, c00.y, c10.y, c01.y, c11.y, e00.y, e10.y, e01.y, e11.y);
+                tri_set<T>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
+            }
+            bool have_next = false;
+            while (true) {
+                if (!have_next && k + 2 <= nw - 1) {
+                    const V4* p2 = p + 2 * plane;
+                    n00 = GridT<T>::ld(p2); n10 = GridT<T>::ld(p2 + 1); n01 = GridT<T>::ld(p2 + nu); n11 = GridT<T>::ld(p2 + nu + 1);
+                    have_next = true;
+                }
+                // ---- stage 1 and the length of this step -------------------------------------------
+                T q = trcp<T>(dw), hq = hw * q;
+                bool ok = dw > T(TT_MARCH_MIN_DW);
+                const T aU = ru * du * q, aV = rv * dv * q;
+                const T adu = tri_eval<T>(qx, tu, tv, fw) * hq, adv = tri_eval<T>(qy, tu, tv, fw) * hq,
+                        adw = tri_eval<T>(qz, tu, tv, fw) * hq, as = hq;
+                const T fw_t = SPC1 ? T(1) : ((j + 1 == spc) ? T(1) : (T)(j + 1) * hsub);
+                T h = fw_t - fw;
+                int cross = 0;                         // +-1: u face, +-2: v face
+                {
+                    const T pu = tfma(h, aU, tu), pv = tfma(h, aV, tv);
+                    if (pu > T(1) || pu < T(0) || pv > T(1) || pv < T(0)) {
+                        T lu = T(2), lv = T(2);
+                        if (aU > T(0)) lu = (T(1) - tu) / (h * aU); else if (aU < T(0)) lu = -tu / (h * aU);
+                        if (aV > T(0)) lv = (T(1) - tv) / (h * aV); else if (aV < T(0)) lv = -tv / (h * aV);
+                        T lam = fmin(lu, lv);
+                        if (lam < T(1)) {
+                            cross = lu <= lv ? (aU > T(0) ? 1 : -1) : (aV > T(0) ? 2 : -2);
+                            h *= lam > T(0) ? lam : T(0);
+                        }
+                    }
+                }
+                const T half = T(0.5) * h;
+                // ---- stages 2-4 ---------------------------------------------------------------------
+                T su = tfma(half, aU, tu), sv = tfma(half, aV, tv), sw = fw + half;
+                T du2 = tfma(half, adu, du), dv2 = tfma(half, adv, dv), dw2 = tfma(half, adw, dw);
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
+                const T bU = ru * du2 * q, bV = rv * dv2 * q;
+                const T bdu = tri_eval<T>(qx, su, sv, sw) * hq, bdv = tri_eval<T>(qy, su, sv, sw) * hq,
+                        bdw = tri_eval<T>(qz, su, sv, sw) * hq, bs = hq;
+                su = tfma(half, bU, tu); sv = tfma(half, bV, tv);
+                du2 = tfma(half, bdu, du); dv2 = tfma(half, bdv, dv); dw2 = tfma(half, bdw, dw);
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
+                const T cU = ru * du2 * q, cV = rv * dv2 * q;
+                const T cdu = tri_eval<T>(qx, su, sv, sw) * hq, cdv = tri_eval<T>(qy, su, sv, sw) * hq,
+                        cdw = tri_eval<T>(qz, su, sv, sw) * hq, cs = hq;
+                su = tfma(h, cU, tu); sv = tfma(h, cV, tv); sw = fw + h;
+                du2 = tfma(h, cdu, du); dv2 = tfma(h, cdv, dv); dw2 = tfma(h, cdw, dw);
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
+                const T eU = ru * du2 * q, eV = rv * dv2 * q;
+                const T edu = tri_eval<T>(qx, su, sv, sw) * hq, edv = tri_eval<T>(qy, su, sv, sw) * hq,
+                        edw = tri_eval<T>(qz, su, sv, sw) * hq, es = hq;
+                const T h6 = h * T(1.0 / 6.0);
+                tu = tfma(h6, aU + T(2) * (bU + cU) + eU, tu);
+                tv = tfma(h6, aV + T(2) * (bV + cV) + eV, tv);
+                du = tfma(h6, adu + T(2) * (bdu + cdu) + edu, du);
+                dv = tfma(h6, adv + T(2) * (bdv + cdv) + edv, dv);
+                dw = tfma(h6, adw + T(2) * (bdw + cdw) + edw, dw);
+                if (track_s) s = tfma(h6, as + T(2) * (bs + cs) + es, s);
+                if (!(ok && dw > T(TT_MARCH_MIN_DW))) { fast = false; break; }   // steep / turning / NaN
+                if (cross == 0) {
+                    // ---- reached the next (sub-)plane ---------------------------------------------
+                    ++steps;
+                    fw = fw_t;
+                    if (SPC1 || ++j == spc) {
+                        j = 0; fw = T(0);
+                        if (++k >= nw - 1) break;                                     // far face: done
+                        p += plane;
+                        if (k + 1 <= nw - 1) {
+                            tri_advance<T>(qx, n00.x, n10.x, n01.x, n11.x);
+                            tri_advance<T>(qy, n00.y, n10.y, n01.y, n11.y);
+                            tri_advance<T>(qz, n00.z, n10.z, n01.z, n11.z);
+                        }
+                        have_next = false;
+                    }
+                } else {
+                    // ---- reached a u / v cell face inside the w-cell: relabel and reload ---------
+                    fw += h;
+                    if (cross == 1) { ++cu; tu -= T(1); } else if (cross == -1) { --cu; tu += T(1); }
+                    else if (cross == 2) { ++cv; tv -= T(1); } else { --cv; tv += T(1); }
+                    if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }   // side exit
+                    p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
+                    V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+                    const V4* p1 = p + plane;
+                    V4 e00 = GridT<T>::ld(p1), e10 = GridT<T>::ld(p1 + 1), e01 = GridT<T>::ld(p1 + nu), e11 = GridT<T>::ld(p1 + nu + 1);
+                    tri_set<T>(qx, c00.x, c10.x, c01.x, c11.x, e00.x, e10.x, e01.x, e11.x);
+                    tri_set<T>(qy, c00.y, c10.y, c01.y, c11.y, e00.y, e10.y, e01.y, e11.y);
+                    tri_set<T>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
+                    have_next = false;
+                }
+            }
+        }
+        if (!fast) {
+            status[ray] = TT_RAY_DEFERRED;          // the general kernel redoes this ray from s0
+            steps = 0;
+        } else {
+            // ---- epilogue: ray_at_exit (particle_tracker.py:345-380) and state at time T ---------
+            const double Pu = A.o[0] + ((double)cu + (double)tu) * A.h[0];
+            const double Pv = A.o[1] + ((double)cv + (double)tv) * A.h[1];
+            const double Pw = A.o[2] + (double)(nw - 1) * A.h[2];
+            const double Vu = (double)du * kC, Vv = (double)dv * kC, Vw = (double)dw * kC;
+            const double tb = (Pw - A.extent) / Vw;
+            rf[0 * A.np + ray] = Pu - Vu * tb;
+            rf[1 * A.np + ray] = atan(Vu / Vw);
+            rf[2 * A.np + ray] = Pv - Vv * tb;
+            rf[3 * A.np + ray] = atan(Vv / Vw);
+            if (sf) {
+                const double t_rest = (A.s_max - (double)s) / kC;
+                const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    sf[(size_t)A.fa[m] * A.np + ray] = Pf[m] + Vf[m] * t_rest;
+                    sf[(size_t)(3 + A.fa[m]) * A.np + ray] = Vf[m];
+                }
+            }
+            status[ray] = (uint8_t)TT_RAY_EXIT_FACE;
+        }
+    }
+    if (ray_steps) {
+        unsigned v = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
+    }
+}
+
 // ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at arbitrary points,
 // zero outside, faces inclusive (scipy _rgi.py:635-642).
 template <typename T>
@@ -660,12 +887,31 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     const long blocks = (np + block - 1) / block;
     TT_REQUIRE(blocks < (1L << 31), "tt_trace: too many rays for one launch");
     cudaStream_t s = (cudaStream_t)stream;
-    TT_REQUIRE(p->variant == 0 || p->variant == 1, "tt_trace: unknown kernel variant %d", p->variant);
+    // variant: 0 = auto (event marching when a status buffer is given, else the cell-cache kernel),
+    //          1 = 8-corner gather per stage, 2 = cell cache, 3 = event marching (needs status_dev)
+    int variant = p->variant;
+    TT_REQUIRE(variant >= 0 && variant <= 3, "tt_trace: unknown kernel variant %d", variant);
+    TT_REQUIRE(variant != 3 || status_dev, "tt_trace: variant 3 (event marching) needs status_dev");
+    if (variant == 0) variant = status_dev ? 3 : 2;
+    int only_flagged = 0;
+    if (variant == 3) {
+        const bool spc1 = p->steps_per_cell == 1;
+#define TT_LAUNCH_EV(TYPE, V4T, S1)                                                                                \
+    trace_event_kernel<TYPE, S1><<<(unsigned)blocks, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev, \
+                                                                     sf_dev, ray_steps_dev, status_dev, A)
+        if (p->dtype == TT_F32) { if (spc1) TT_LAUNCH_EV(float, float4, true); else TT_LAUNCH_EV(float, float4, false); }
+        else { if (spc1) TT_LAUNCH_EV(double, double4, true); else TT_LAUNCH_EV(double, double4, false); }
+#undef TT_LAUNCH_EV
+        int rc2 = launch_check("trace_event_kernel");
+        if (rc2) return rc2;
+        only_flagged = 1;          // second pass: the general kernel on the deferred rays only
+        variant = 2;
+    }
 #define TT_LAUNCH(TYPE, V4T, VAR)                                                                                 \
     trace_kernel<TYPE, VAR><<<(unsigned)blocks, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev,    \
-                                                                sf_dev, ray_steps_dev, status_dev, A)
-    if (p->dtype == TT_F32) { if (p->variant == 1) TT_LAUNCH(float, float4, 1); else TT_LAUNCH(float, float4, 0); }
-    else { if (p->variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
+                                                                sf_dev, ray_steps_dev, status_dev, A, only_flagged)
+    if (p->dtype == TT_F32) { if (variant == 1) TT_LAUNCH(float, float4, 1); else TT_LAUNCH(float, float4, 0); }
+    else { if (variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
 #undef TT_LAUNCH
     return launch_check("trace_kernel");
 }

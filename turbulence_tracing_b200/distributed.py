@@ -110,15 +110,19 @@ def allreduce_scalar(value, op: str = "sum", device=None):
     return t.item()
 
 
-def trace_sharded(cube, detectors, n_total, beam_size, divergence, seed, bundle=None, histogram_kw=None):
+def trace_sharded(cube, detectors, n_total, beam_size, divergence, seed, bundle=None, histogram_kw=None,
+                  rank=None, world=None, reduce=True):
     """The reference's ``full_system_solve`` loop (example_MPI.py:48-79, 117-141) on this rank's shard
     of one global beam, followed by the single histogram all-reduce.
 
     cube: ElectronCube with its gradient grid built.  detectors: list of (cls, ctor_kwargs,
     solve_kwargs).  bundle: rays per launch (memory knob, the reference's Np_ray_split).
+    rank/world override the process group's (to compute one shard's contribution in a single process;
+    combine with reduce=False).
     Returns (list of reduced int64 histograms [device], total ray-steps over all ranks)."""
     import torch
-    rank, world = rank_world()
+    if rank is None or world is None:
+        rank, world = rank_world()
     first, count = shard_range(n_total, rank, world)
     bundle = int(bundle or max(count, 1))
     histogram_kw = histogram_kw or {}
@@ -142,6 +146,8 @@ def trace_sharded(cube, detectors, n_total, beam_size, divergence, seed, bundle=
             pix_x, pix_y = histogram_kw.get("pix_x", 3448), histogram_kw.get("pix_y", 2574)
             bs = histogram_kw.get("bin_scale", 10)
             acc.append(torch.zeros((pix_y // bs, pix_x // bs), dtype=torch.int64, device="cuda"))
+    if not reduce:
+        return acc, int(steps)
     reduced = allreduce_histograms(acc)
     total_steps = allreduce_scalar(int(steps), "sum", device=reduced[0].device if reduced else None)
     return reduced, total_steps

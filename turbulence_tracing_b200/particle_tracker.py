@@ -318,7 +318,8 @@ class ElectronCube:
         rf = torch.empty((4, Np), dtype=torch.float64, device="cuda")
         sf = torch.empty((6, Np), dtype=torch.float64, device="cuda") if self.keep_sf else None
         steps = torch.zeros(1, dtype=torch.int64, device="cuda")
-        status = torch.empty(Np, dtype=torch.uint8, device="cuda") if return_status else None
+        # always passed: the default kernel (event marching) flags rays for its second pass here
+        status = torch.empty(Np, dtype=torch.uint8, device="cuda")
         events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
         if events is not None:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -338,7 +339,7 @@ class ElectronCube:
         self.sf = DeviceArray(sf) if sf is not None else None
         self.rf = DeviceArray(rf)
         self.rf.perm = perm        # lets the detectors visit the rays in Morton order
-        self.status = DeviceArray(status) if status is not None else None
+        self.status = DeviceArray(status)
         return self.rf
 
     @property

@@ -29,6 +29,35 @@ def _sqrt_spectrum_table(N, k_func):
     return lut
 
 
+def _gaussian_fft(ndim, N, k_func, seed, dtype, Wr, Wi, return_device):
+    torch = _lib.torch_cuda()
+    lib = _lib.load()
+    N = int(N)
+    M = 2 * N + 1
+    shape = (M,) * ndim
+    code = _lib.dtype_code(dtype)
+    tdt = torch.float64 if code == _lib.TT_F64 else torch.float32
+    lut = torch.from_numpy(_sqrt_spectrum_table(N, k_func)).cuda()
+    wr = wi = None
+    if seed is None or Wr is not None:
+        if Wr is None:
+            Wr = np.random.randn(*shape)        # draw order of the reference: Wr, then Wi
+            Wi = np.random.randn(*shape)
+        wr = _lib.to_device(Wr, torch.float64)
+        wi = _lib.to_device(Wi, torch.float64)
+        if tuple(wr.shape) != shape or tuple(wi.shape) != shape:
+            raise ValueError(f"Wr and Wi must have shape {shape}")
+    need = C.c_size_t(0)
+    _lib.check(lib.tt_grf_nd_workspace(ndim, N, code, C.byref(need)), "tt_grf_nd_workspace")
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    out = torch.empty(shape, dtype=tdt, device="cuda")
+    _lib.check(lib.tt_grf_nd(ndim, N, code, _lib.ptr(lut), _lib.ptr(wr), _lib.ptr(wi), int(seed or 0), _lib.ptr(out),
+                             _lib.ptr(ws), need.value, _lib.stream_ptr()), "tt_grf_nd")
+    if return_device:
+        return DeviceArray(out)
+    return out.cpu().numpy()
+
+
 def gaussian3D_FFT(N, k_func, *, seed=None, dtype="float64", Wr=None, Wi=None, return_device=False):
     """A FFT based generator for scalar Gaussian fields in 3D (:488-538).
 
@@ -38,28 +67,14 @@ def gaussian3D_FFT(N, k_func, *, seed=None, dtype="float64", Wr=None, Wi=None, r
     ``np.random.randn(M, M, M)`` in the reference's order (Wr then Wi, :522-523), so that the result
     equals the reference's for the same numpy seed (to FFT rounding).  With ``seed`` the noise comes
     from the device Philox generator and nothing of size M^3 ever touches the host."""
-    torch = _lib.torch_cuda()
-    lib = _lib.load()
-    N = int(N)
-    M = 2 * N + 1
-    code = _lib.dtype_code(dtype)
-    tdt = torch.float64 if code == _lib.TT_F64 else torch.float32
-    lut = torch.from_numpy(_sqrt_spectrum_table(N, k_func)).cuda()
-    wr = wi = None
-    if seed is None or Wr is not None:
-        if Wr is None:
-            Wr = np.random.randn(M, M, M)
-            Wi = np.random.randn(M, M, M)
-        wr = _lib.to_device(Wr, torch.float64)
-        wi = _lib.to_device(Wi, torch.float64)
-        if tuple(wr.shape) != (M, M, M) or tuple(wi.shape) != (M, M, M):
-            raise ValueError("Wr and Wi must have shape (2N+1,)*3")
-    need = C.c_size_t(0)
-    _lib.check(lib.tt_grf_workspace(N, code, C.byref(need)), "tt_grf_workspace")
-    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
-    out = torch.empty((M, M, M), dtype=tdt, device="cuda")
-    _lib.check(lib.tt_grf3d(N, code, _lib.ptr(lut), _lib.ptr(wr), _lib.ptr(wi), int(seed or 0), _lib.ptr(out),
-                            _lib.ptr(ws), need.value, _lib.stream_ptr()), "tt_grf3d")
-    if return_device:
-        return DeviceArray(out)
-    return out.cpu().numpy()
+    return _gaussian_fft(3, N, k_func, seed, dtype, Wr, Wi, return_device)
+
+
+def gaussian2D_FFT(N, k_func, *, seed=None, dtype="float64", Wr=None, Wi=None, return_device=False):
+    """2-D variant, domain (2N+1)^2 (:436-486)."""
+    return _gaussian_fft(2, N, k_func, seed, dtype, Wr, Wi, return_device)
+
+
+def gaussian1D_FFT(N, k_func, *, seed=None, dtype="float64", Wr=None, Wi=None, return_device=False):
+    """1-D variant, domain 2N+1 (:388-434)."""
+    return _gaussian_fft(1, N, k_func, seed, dtype, Wr, Wi, return_device)
