@@ -112,6 +112,27 @@ int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_d
              const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
              unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
 
+/* ---- magnetised / absorbing extension (BASELINE config 4) --------------------------------------
+ * Evidence in the reference: call sites only (example_kitchensink.py:72-101: B_on, inv_brems,
+ * phaseshift, external_B/Te/Z, Jf) -- there is no implementation in the checkout, so parity is
+ * UNPINNED; textbook forms are used.  Along each ray, with s = c t, d = v/c:
+ *   phase     dphi/ds   = (omega/c)(sqrt(1 - ne/nc) - 1)
+ *   Faraday   dalpha/ds = verdet * ne * (B . d)        verdet = e^3 lambda^2/(8 pi^2 eps0 me^2 c^3)
+ *   inverse bremsstrahlung  dln(a)/ds = -kappa/2       kappa = energy absorption coefficient (1/m)
+ * aux4_dev: second grid (B_u, B_v, B_w, kappa) in the gradient grid's layout and dtype (nullable:
+ * phase only).  aux_out_dev[3][np] = (amplitude factor, phase [rad], rotation [rad]).  Same
+ * trajectory integration, outputs and edge-case handling as tt_trace (gather kernel).            */
+typedef struct tt_aux_params {
+    double omega;   /* laser angular frequency (rad/s)        */
+    double nc;      /* critical density (m^-3)                */
+    double verdet;  /* rad / (T m^2): rotation = verdet * int ne B_par ds */
+} tt_aux_params;
+
+int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* grid4_dev,
+                 const void* aux4_dev, const double* s0_dev, long np, const uint32_t* perm_dev,
+                 double* rf_dev, double* sf_dev, double* aux_out_dev,
+                 unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
+
 /* ---- K5+K6: ray_transfer_matrix.py optics (:37-154), detector programs (:208-299) and
  *      Rays.histogram (:173-195) ---------------------------------------------------------------
  * One pass over the rays: scale positions (pos_scale = 1e3 is m_to_mm, :37-40), run the element

@@ -560,3 +560,151 @@ def test_two_gpu_nccl_histogram_equals_one_gpu(tt, tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+# ------------------------------------------------------------------------------------------- config 4
+# Magnetised / absorbing extension.  PARITY UNPINNED against the reference (call sites only,
+# example_kitchensink.py:72-101): checked against closed forms and an independent FP64 scipy
+# integration of the same textbook equations (oracle.solve_aux).
+def _aux_cube(tt, x, ne, B, Te, dtype, spc, **kw):
+    pt = tt.particle_tracker
+    cube = pt.ElectronCube(x, x, x, B_on=B is not None, inv_brems=Te is not None, phaseshift=True, dtype=dtype,
+                           steps_per_cell=spc, verbose=False, **kw)
+    cube.external_ne(ne)
+    if B is not None:
+        cube.external_B(B)
+    if Te is not None:
+        cube.external_Te(Te)
+        cube.external_Z(2.0)
+    cube.calc_dndr()
+    cube.set_up_interps()
+    return cube
+
+
+@pytest.mark.parametrize("direction", ["z", "y"])
+def test_aux_uniform_plasma_closed_forms(tt, direction):
+    pt = tt.particle_tracker
+    n = 41
+    x = np.linspace(-5e-3, 5e-3, n)
+    ne = np.full((n, n, n), 1e25)
+    B = np.zeros((n, n, n, 3))
+    B[..., 0], B[..., 1], B[..., 2] = 0.3, -0.2, 10.0
+    Te = np.full((n, n, n), 100.0)
+    cube = pt.ElectronCube(x, x, x, direction, B_on=True, inv_brems=True, phaseshift=True, dtype="float64",
+                           steps_per_cell=1, verbose=False)
+    cube.external_ne(ne); cube.external_B(B); cube.external_Te(Te); cube.external_Z(2.0)
+    cube.calc_dndr()
+    np.random.seed(1)
+    cube.init_beam(2000, 3e-3, 20e-3)
+    rf = np.asarray(cube.solve())
+    s0 = cube.s0
+    par = "xyz".index(direction)
+    d = s0[3:] / orc.C_LIGHT
+    L = 10e-3
+    path = L / d[par]
+    omega, nc = orc.critical_density()
+    np.testing.assert_allclose(np.asarray(cube.phase), omega / orc.C_LIGHT * (np.sqrt(1 - 1e25 / nc) - 1) * path, rtol=1e-12)
+    Bd = 0.3 * d[0] - 0.2 * d[1] + 10.0 * d[2]
+    np.testing.assert_allclose(np.asarray(cube.pol), pt.VERDET * 1053e-9**2 * 1e25 * Bd * path, rtol=1e-11)
+    kap = float(cube.kappa()[0, 0, 0])
+    lnL = max(2.0, 24 - np.log(np.sqrt(1e19) / 100.0))
+    assert kap == pytest.approx(100 * 3.1e-7 * 2 * 1e19**2 * lnL * 100.0**-1.5 / omega**2 / np.sqrt(1 - 1e25 / nc), rel=1e-12)
+    np.testing.assert_allclose(np.asarray(cube.amp), np.exp(-0.5 * kap * path), rtol=1e-12)
+    # straight rays; Jones vector as example_kitchensink.py:99-101 reads it
+    t1 = [a for a in range(3) if a != par][0]
+    np.testing.assert_allclose(rf[1], np.arctan(d[t1] / d[par]), rtol=0, atol=1e-15)
+    J = cube.Jf
+    assert J.shape == (2, 2000) and np.iscomplexobj(J)
+    np.testing.assert_allclose(np.arctan(np.real(J[0] / J[1])), np.asarray(cube.pol), rtol=1e-9)
+    np.testing.assert_allclose(np.sqrt(np.abs(J[0]) ** 2 + np.abs(J[1]) ** 2), np.asarray(cube.amp), rtol=1e-12)
+    # 9-row s0 (old init_beam layout: amplitude, phase, polarisation rows)
+    s9 = np.vstack([s0, np.full((1, 2000), 0.5), np.full((1, 2000), 0.25), np.full((1, 2000), -0.1)])
+    amp0, ph0, pol0 = (np.asarray(a).copy() for a in (cube.amp, cube.phase, cube.pol))
+    cube.s0 = s9
+    cube.solve()
+    np.testing.assert_allclose(np.asarray(cube.amp), 0.5 * amp0, rtol=1e-14)
+    np.testing.assert_allclose(np.asarray(cube.phase), 0.25 + ph0, rtol=1e-14)
+    np.testing.assert_allclose(np.asarray(cube.pol), -0.1 + pol0, rtol=1e-13)
+
+
+def test_aux_random_fields_match_scipy_integration(tt, golden):
+    g = golden("trace_grf33")
+    x, ne = g["x"], g["ne"]
+    rng = np.random.RandomState(4)
+    n = len(x)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    B = np.stack([2 * np.sin(400 * Y) + 0.5, 3 * np.cos(300 * X * 1.0) - 1.0, 10 + 4 * np.sin(500 * Z + 300 * X)], axis=-1)
+    Te = 80 + 40 * np.cos(250 * X) * np.sin(350 * Y)
+    s0 = g["s0"][:, :32]
+    res = {}
+    for dtype, spc in (("float64", 8), ("float32", 4)):
+        cube = _aux_cube(tt, x, ne, B, Te, dtype, spc)
+        cube.s0 = s0
+        cube.extent = float(g["extent"])
+        rf = np.asarray(cube.solve())
+        res[dtype] = (rf, np.asarray(cube.amp), np.asarray(cube.phase), np.asarray(cube.pol))
+        kappa = cube.kappa().cpu().numpy()
+    rf_o, amp_o, ph_o, pol_o = orc.solve_aux(ne, B, kappa, x, x, x, s0, float(g["extent"]), rtol=1e-10, atol=1e-13, batch=16)
+    rf, amp, ph, pol = res["float64"]
+    assert np.abs(ph_o).min() > 100 and np.abs(pol_o).max() > 0.05 and amp_o.max() < 0.9999
+    print(f"aux fp64: phase err {np.abs(ph - ph_o).max():.2e} rad of {np.abs(ph_o).max():.0f}, rotation err "
+          f"{np.abs(pol - pol_o).max():.2e} of {np.abs(pol_o).max():.3f}, amplitude err {np.abs(amp - amp_o).max():.2e}")
+    np.testing.assert_allclose(rf[0], rf_o[0], rtol=0, atol=1e-5 * 4e-3)
+    np.testing.assert_allclose(ph, ph_o, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(pol, pol_o, rtol=0, atol=1e-5 * np.abs(pol_o).max())
+    np.testing.assert_allclose(amp, amp_o, rtol=1e-6)
+    rf32, amp32, ph32, pol32 = res["float32"]
+    print(f"aux fp32: phase err {np.abs(ph32 - ph_o).max():.2e} rad, rotation err {np.abs(pol32 - pol_o).max():.2e}")
+    np.testing.assert_allclose(ph32, ph_o, rtol=0, atol=5e-3)
+    np.testing.assert_allclose(pol32, pol_o, rtol=0, atol=1e-4 * np.abs(pol_o).max())
+    np.testing.assert_allclose(amp32, amp_o, rtol=1e-5)
+
+
+def test_aux_flags_and_errors(tt):
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 17)
+    ne = np.full((17, 17, 17), 5e24)
+    cube = pt.ElectronCube(x, x, x, phaseshift=True, verbose=False)          # phase only: no second grid
+    cube.external_ne(ne)
+    cube.calc_dndr()
+    cube.init_beam(100, 1e-3, 0.0, seed=1)
+    cube.solve()
+    omega, nc = orc.critical_density()
+    np.testing.assert_allclose(np.asarray(cube.phase), omega / orc.C_LIGHT * (np.sqrt(1 - 5e24 / nc) - 1) * 10e-3, rtol=2e-6)
+    assert np.all(np.asarray(cube.pol) == 0) and np.all(np.asarray(cube.amp) == 1)
+    c2 = pt.ElectronCube(x, x, x, B_on=True, verbose=False)
+    c2.external_ne(ne)
+    c2.calc_dndr()
+    c2.init_beam(10, 1e-3, 0.0, seed=1)
+    with pytest.raises(AttributeError):
+        c2.solve()                                   # B_on without external_B
+    c3 = pt.ElectronCube.legacy(x, x, x, 5e-3, B_on=False, inv_brems=False, phaseshift=False, probing_direction="y")
+    assert c3.probing_direction == "y"
+    with pytest.raises(AttributeError):
+        _ = pt.ElectronCube(x, x, x).Jf
+
+
+def test_refractometer_images_position_in_x_and_angle_in_y(tt):
+    """Imaging refractometer (unpinned: composed from the reference's elements): x_det = 2 x0, y_det = -L phi0."""
+    rtm = tt.ray_transfer_matrix
+    rng = np.random.RandomState(2)
+    n = 5000
+    r0 = np.zeros((4, n))
+    r0[0], r0[2] = rng.uniform(-2e-3, 2e-3, n), rng.uniform(-2e-3, 2e-3, n)
+    r0[1], r0[3] = 3e-3 * rng.randn(n), 3e-3 * rng.randn(n)
+    d = rtm.BurdiscopeRays(r0, L=400, R=25, Lx=18, Ly=13.5)
+    d.solve()
+    rf = np.asarray(d.rf)
+    ok = ~np.isnan(rf[0])
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(rf[0][ok], 2 * 1e3 * r0[0][ok], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(rf[2][ok], -400 * r0[3][ok], rtol=0, atol=1e-9)
+    # the same program written with the public element functions
+    r = rtm.m_to_mm(r0)
+    r = rtm.distance(r, 400); r = rtm.circular_aperture(r, 25); r = rtm.sym_lens(r, 400); r = rtm.distance(r, 800)
+    r = rtm.circular_aperture(r, 25); r = rtm.sym_lens(r, 400); r = rtm.distance(r, 600)
+    r = rtm.rect_aperture(r, 25, 25); r = rtm.lens(r, 400 / 3, 400); r = rtm.distance(r, 400)
+    np.testing.assert_allclose(np.asarray(r), rf, rtol=1e-12, atol=1e-12, equal_nan=True)
+    d.histogram(bin_scale=10)
+    assert d.H.sum() == np.sum(ok & (np.abs(rf[0]) <= 9) & (np.abs(rf[2]) <= 6.75))
+    assert rtm.ShadowgraphyRays is rtm.Shadowgraphy and rtm.SchlierenRays is rtm.Schlieren_DF

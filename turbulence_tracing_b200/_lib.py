@@ -39,6 +39,10 @@ class TraceParams(C.Structure):
     ]
 
 
+class AuxParams(C.Structure):
+    _fields_ = [("omega", C.c_double), ("nc", C.c_double), ("verdet", C.c_double)]
+
+
 class Optic(C.Structure):
     _fields_ = [("op", C.c_int), ("pad_", C.c_int), ("a", C.c_double), ("b", C.c_double)]
 
@@ -58,6 +62,8 @@ PROTOTYPES = {
     "tt_sort_rays_workspace": (_i, [_l, C.POINTER(_sz)]),
     "tt_sort_rays": (_i, [_vp, _l, _i, C.POINTER(_D3), C.POINTER(_D3), C.POINTER(_I3), _vp, _vp, _sz, _vp]),
     "tt_trace": (_i, [C.POINTER(TraceParams), _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
+                          _vp, _vp]),
     "tt_optics_hist": (_i, [_vp, _l, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_optics_hist_perm": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_grf_workspace": (_i, [_i, _i, C.POINTER(_sz)]),

@@ -117,17 +117,88 @@ struct Consts {
     T iu_, iv_, iw_;  // 1/hu, 1/hv, 1/hw  (arc-length stepping)
 };
 
+// ---- passive quantities carried along the ray (BASELINE config 4; no implementation in the reference
+// checkout -- only call sites, example_kitchensink.py:72-101 -- so parity is unpinned; textbook forms):
+//   phase          dphi/ds   = (omega/c) (n - 1),        n = sqrt(1 - ne/nc)
+//   Faraday        dalpha/ds = V ne (B . d),              V = e^3 lambda^2 / (8 pi^2 eps0 me^2 c^3)
+//   inv. brems.    dln(a)/ds = -kappa / 2                 (kappa: energy absorption coefficient, 1/m)
+// with s = c t and d = v/c.  They do not act back on the trajectory, so the RK4 stages of the ray are
+// reused as a Simpson quadrature (weights 1, 2, 2, 1).  aux4 = (B_u, B_v, B_w, kappa) on the same grid
+// layout as the gradient grid, whose 4th lane is ne/nc.  Accumulated in FP64; scaled by the constants
+// in the epilogue.
+template <typename T>
+struct AuxCtx {
+    const typename GridT<T>::V4* aux4;     // may be null: phase only
+    double phase, farad, absorb;           // integrals of (n-1), (ne/nc)(B.d), kappa over s
+};
+
+template <typename T>
+__device__ __forceinline__ void trilinear_w(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
+                                            int cu, int cv, int cw, T tu, T tv, T tw, T& w_only) {
+    typedef typename GridT<T>::V4 V4;
+    const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
+    T c000 = GridT<T>::ld(p).w, c100 = GridT<T>::ld(p + 1).w, c010 = GridT<T>::ld(p + nu).w, c110 = GridT<T>::ld(p + nu + 1).w;
+    p += plane;
+    T c001 = GridT<T>::ld(p).w, c101 = GridT<T>::ld(p + 1).w, c011 = GridT<T>::ld(p + nu).w, c111 = GridT<T>::ld(p + nu + 1).w;
+    T a00 = tfma(tu, c100 - c000, c000), a10 = tfma(tu, c110 - c010, c010);
+    T a01 = tfma(tu, c101 - c001, c001), a11 = tfma(tu, c111 - c011, c011);
+    T b0 = tfma(tv, a10 - a00, a00), b1 = tfma(tv, a11 - a01, a01);
+    w_only = tfma(tw, b1 - b0, b0);
+}
+
+template <typename T>
+__device__ __forceinline__ void trilinear4(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
+                                           int cu, int cv, int cw, T tu, T tv, T tw, T& x, T& y, T& z, T& w) {
+    typedef typename GridT<T>::V4 V4;
+    const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
+    V4 c000 = GridT<T>::ld(p), c100 = GridT<T>::ld(p + 1), c010 = GridT<T>::ld(p + nu), c110 = GridT<T>::ld(p + nu + 1);
+    p += plane;
+    V4 c001 = GridT<T>::ld(p), c101 = GridT<T>::ld(p + 1), c011 = GridT<T>::ld(p + nu), c111 = GridT<T>::ld(p + nu + 1);
+#define TT_TRI4(m, out)                                                  \
+    {                                                                    \
+        T a00 = tfma(tu, c100.m - c000.m, c000.m);                       \
+        T a10 = tfma(tu, c110.m - c010.m, c010.m);                       \
+        T a01 = tfma(tu, c101.m - c001.m, c001.m);                       \
+        T a11 = tfma(tu, c111.m - c011.m, c011.m);                       \
+        T b0 = tfma(tv, a10 - a00, a00);                                 \
+        T b1 = tfma(tv, a11 - a01, a01);                                 \
+        out = tfma(tw, b1 - b0, b0);                                     \
+    }
+    TT_TRI4(x, x) TT_TRI4(y, y) TT_TRI4(z, z) TT_TRI4(w, w)
+#undef TT_TRI4
+}
+
+// integrands at one stage, multiplied by `scale` (ds/dW = hw/dw when marching in W, 1 in path time)
+template <typename T>
+__device__ __forceinline__ void aux_rates(const AuxCtx<T>& ctx, const typename GridT<T>::V4* __restrict__ grid,
+                                          const Consts<T>& C, int cu, int cv, int cw, T tu, T tv, T tw, T du, T dv,
+                                          T dw, T scale, double& fp, double& ff, double& fa) {
+    T nn;
+    trilinear_w<T>(grid, C.nu, C.plane, cu, cv, cw, tu, tv, tw, nn);       // ne/nc
+    const double nr = 1.0 - (double)nn;
+    fp = (sqrt(nr > 0.0 ? nr : 0.0) - 1.0) * (double)scale;
+    ff = 0.0; fa = 0.0;
+    if (ctx.aux4) {
+        T bu, bv, bw, kap;
+        trilinear4<T>(ctx.aux4, C.nu, C.plane, cu, cv, cw, tu, tv, tw, bu, bv, bw, kap);
+        ff = (double)nn * ((double)bu * du + (double)bv * dv + (double)bw * dw) * (double)scale;
+        fa = (double)kap * (double)scale;
+    }
+}
+
 // One RK4 step in W from fraction fwa to fwa + h inside w-cell k (0 <= fwa, fwa + h <= 1).
 // Updates fu, fv (un-normalised), d and s of r.  Returns false if a stage saw d_w <= 0.
-template <typename T>
+template <typename T, bool AUX = false>
 __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
-                                      Ray<T>& r, int k, T fwa, T h) {
+                                      Ray<T>& r, int k, T fwa, T h, AuxCtx<T>* ctx = nullptr) {
     const T half = T(0.5) * h;
     int cu, cv; T tu, tv;
+    double fp[4], ff[4], fa[4];
     // stage 1
     cell_of(r.iu, r.fu, C.nu, cu, tu); cell_of(r.iv, r.fv, C.nv, cv, tv);
     G3<T> g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa);
     T inv = C.hw / r.dw;
+    if (AUX) aux_rates<T>(*ctx, grid, C, cu, cv, k, tu, tv, fwa, r.du, r.dv, r.dw, inv, fp[0], ff[0], fa[0]);
     T aU = C.ru * r.du / r.dw, aV = C.rv * r.dv / r.dw;
     T adu = g.x * inv, adv = g.y * inv, adw = g.z * inv, as = inv;
     bool ok = r.dw > T(0);
@@ -137,6 +208,7 @@ __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ 
     g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa + half);
     ok = ok && dw > T(0);
     inv = C.hw / dw;
+    if (AUX) aux_rates<T>(*ctx, grid, C, cu, cv, k, tu, tv, fwa + half, du, dv, dw, inv, fp[1], ff[1], fa[1]);
     T bU = C.ru * du / dw, bV = C.rv * dv / dw;
     T bdu = g.x * inv, bdv = g.y * inv, bdw = g.z * inv, bs = inv;
     // stage 3
@@ -145,6 +217,7 @@ __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ 
     g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwa + half);
     ok = ok && dw > T(0);
     inv = C.hw / dw;
+    if (AUX) aux_rates<T>(*ctx, grid, C, cu, cv, k, tu, tv, fwa + half, du, dv, dw, inv, fp[2], ff[2], fa[2]);
     T cU = C.ru * du / dw, cV = C.rv * dv / dw;
     T cdu = g.x * inv, cdv = g.y * inv, cdw = g.z * inv, cs = inv;
     // stage 4
@@ -154,6 +227,7 @@ __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ 
     g = trilinear<T>(grid, C.nu, C.plane, cu, cv, k, tu, tv, fwb > T(1) ? T(1) : fwb);
     ok = ok && dw > T(0);
     inv = C.hw / dw;
+    if (AUX) aux_rates<T>(*ctx, grid, C, cu, cv, k, tu, tv, fwb > T(1) ? T(1) : fwb, du, dv, dw, inv, fp[3], ff[3], fa[3]);
     T eU = C.ru * du / dw, eV = C.rv * dv / dw;
     T edu = g.x * inv, edv = g.y * inv, edw = g.z * inv, es = inv;
     const T h6 = h * T(1.0 / 6.0);
@@ -163,28 +237,43 @@ __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ 
     r.dv = tfma(h6, adv + T(2) * (bdv + cdv) + edv, r.dv);
     r.dw = tfma(h6, adw + T(2) * (bdw + cdw) + edw, r.dw);
     r.s = tfma(h6, as + T(2) * (bs + cs) + es, r.s);
+    if (AUX) {
+        const double w6 = (double)h6;
+        ctx->phase += w6 * (fp[0] + 2.0 * (fp[1] + fp[2]) + fp[3]);
+        ctx->farad += w6 * (ff[0] + 2.0 * (ff[1] + ff[2]) + ff[3]);
+        ctx->absorb += w6 * (fa[0] + 2.0 * (fa[1] + fa[2]) + fa[3]);
+    }
     return ok;
 }
 
 // One RK4 step of length ds in path time (general direction).  Fractions un-normalised after.
-template <typename T>
+template <typename T, bool AUX = false>
 __device__ __forceinline__ void sstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
-                                      Ray<T>& r, T ds) {
+                                      Ray<T>& r, T ds, AuxCtx<T>* ctx = nullptr) {
     const T half = T(0.5) * ds;
     int cu, cv, cw; T tu, tv, tw;
-    auto field = [&](T fu, T fv, T fw) {
+    double fp[4], ff[4], fa[4];
+    int stage = 0;
+    auto field = [&](T fu, T fv, T fw, T du, T dv, T dw) {
         cell_of(r.iu, fu, C.nu, cu, tu); cell_of(r.iv, fv, C.nv, cv, tv); cell_of(r.iw, fw, C.nw, cw, tw);
+        if (AUX) { aux_rates<T>(*ctx, grid, C, cu, cv, cw, tu, tv, tw, du, dv, dw, T(1), fp[stage], ff[stage], fa[stage]); ++stage; }
         return trilinear<T>(grid, C.nu, C.plane, cu, cv, cw, tu, tv, tw);
     };
-    G3<T> g1 = field(r.fu, r.fv, r.fw);
+    G3<T> g1 = field(r.fu, r.fv, r.fw, r.du, r.dv, r.dw);
     T d1u = r.du, d1v = r.dv, d1w = r.dw;
     T d2u = tfma(half, g1.x, r.du), d2v = tfma(half, g1.y, r.dv), d2w = tfma(half, g1.z, r.dw);
-    G3<T> g2 = field(tfma(half * C.iu_, d1u, r.fu), tfma(half * C.iv_, d1v, r.fv), tfma(half * C.iw_, d1w, r.fw));
+    G3<T> g2 = field(tfma(half * C.iu_, d1u, r.fu), tfma(half * C.iv_, d1v, r.fv), tfma(half * C.iw_, d1w, r.fw), d2u, d2v, d2w);
     T d3u = tfma(half, g2.x, r.du), d3v = tfma(half, g2.y, r.dv), d3w = tfma(half, g2.z, r.dw);
-    G3<T> g3 = field(tfma(half * C.iu_, d2u, r.fu), tfma(half * C.iv_, d2v, r.fv), tfma(half * C.iw_, d2w, r.fw));
+    G3<T> g3 = field(tfma(half * C.iu_, d2u, r.fu), tfma(half * C.iv_, d2v, r.fv), tfma(half * C.iw_, d2w, r.fw), d3u, d3v, d3w);
     T d4u = tfma(ds, g3.x, r.du), d4v = tfma(ds, g3.y, r.dv), d4w = tfma(ds, g3.z, r.dw);
-    G3<T> g4 = field(tfma(ds * C.iu_, d3u, r.fu), tfma(ds * C.iv_, d3v, r.fv), tfma(ds * C.iw_, d3w, r.fw));
+    G3<T> g4 = field(tfma(ds * C.iu_, d3u, r.fu), tfma(ds * C.iv_, d3v, r.fv), tfma(ds * C.iw_, d3w, r.fw), d4u, d4v, d4w);
     const T s6 = ds * T(1.0 / 6.0);
+    if (AUX) {
+        const double w6 = (double)s6;
+        ctx->phase += w6 * (fp[0] + 2.0 * (fp[1] + fp[2]) + fp[3]);
+        ctx->farad += w6 * (ff[0] + 2.0 * (ff[1] + ff[2]) + ff[3]);
+        ctx->absorb += w6 * (fa[0] + 2.0 * (fa[1] + fa[2]) + fa[3]);
+    }
     r.fu = tfma(s6 * C.iu_, d1u + T(2) * (d2u + d3u) + d4u, r.fu);
     r.fv = tfma(s6 * C.iv_, d1v + T(2) * (d2v + d3v) + d4v, r.fv);
     r.fw = tfma(s6 * C.iw_, d1w + T(2) * (d2w + d3w) + d4w, r.fw);
@@ -230,9 +319,10 @@ struct March {
 // Plane marching with a full 8-corner gather at every stage (the straightforward kernel; also
 // used for the partial first cell of rays that enter through a side face and for side exits).
 // Marches from (r.iw, r.fw) to the far face, or only to the next integer plane (until_plane).
-template <typename T>
+template <typename T, bool AUX = false>
 __device__ __noinline__ void march_generic(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
-                                           Ray<T>& r, March<T>& m, T s_left0, int spc, bool until_plane) {
+                                           Ray<T>& r, March<T>& m, T s_left0, int spc, bool until_plane,
+                                           AuxCtx<T>* ctx = nullptr) {
     const T hsub = T(1) / (T)spc;
     int k = r.iw;
     T fw = r.fw;
@@ -241,11 +331,14 @@ __device__ __noinline__ void march_generic(const typename GridT<T>::V4* __restri
         T fwb = (j + 1 == spc) ? T(1) : (T)(j + 1) * hsub;
         T h = fwb - fw;
         Ray<T> old = r;
-        bool ok = zstep<T>(grid, C, r, k, fw, h);
+        AuxCtx<T> old_ctx;
+        if (AUX) old_ctx = *ctx;
+        bool ok = zstep<T, AUX>(grid, C, r, k, fw, h, ctx);
         ++m.steps;
         bool bad = !ok || !(r.dw > T(TT_MARCH_MIN_DW)) || !(r.s <= s_left0);
         if (bad) {          // hand the step to the general integrator from the old state
             r = old; r.iw = k; r.fw = fw; --m.steps;
+            if (AUX) *ctx = old_ctx;
             m.general = true;
             return;
         }
@@ -254,8 +347,9 @@ __device__ __noinline__ void march_generic(const typename GridT<T>::V4* __restri
         T lam = fmin(lu, lv);
         if (lam <= T(1)) {   // side exit: re-step to the face, freeze
             r = old;
+            if (AUX) *ctx = old_ctx;
             lam = lam < T(0) ? T(0) : lam;
-            zstep<T>(grid, C, r, k, fw, lam * h);
+            zstep<T, AUX>(grid, C, r, k, fw, lam * h, ctx);
             r.iw = k; r.fw = fw + lam * h;
             clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv);
             m.st |= TT_RAY_EXIT_SIDE;
@@ -431,13 +525,20 @@ __device__ __forceinline__ void march_cached(const typename GridT<T>::V4* __rest
     m.alive = false;
 }
 
-template <typename T, int VARIANT>
+struct AuxArgs {
+    double omega_over_c;    // phase = omega/c * int (n - 1) ds
+    double verdet_nc;       // rotation = V * nc * int (ne/nc) (B . d) ds
+};
+
+template <typename T, int VARIANT, bool AUX = false>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS) trace_kernel(const typename GridT<T>::V4* __restrict__ grid,
                                                     const double* __restrict__ s0,
                                                     const uint32_t* __restrict__ perm,
                                                     double* __restrict__ rf, double* __restrict__ sf,
                                                     unsigned long long* __restrict__ ray_steps,
-                                                    uint8_t* __restrict__ status, TraceArgs A, int only_flagged) {
+                                                    uint8_t* __restrict__ status, TraceArgs A, int only_flagged,
+                                                    const typename GridT<T>::V4* __restrict__ aux4 = nullptr,
+                                                    double* __restrict__ aux_out = nullptr, AuxArgs AX = AuxArgs()) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned steps = 0;
     bool mine = tid < A.np;
@@ -517,10 +618,12 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
         // rays that could run into the path-time cap c*T while marching are integrated by the general
         // loop, which stops exactly at the cap (never the case for the reference's symmetric cubes)
         if (alive && !general && (T)(C.nw - 1 - r.iw) * C.hw > T(TT_MARCH_MIN_DW) * s_left0) general = true;
+        AuxCtx<T> ctx;
+        ctx.aux4 = aux4; ctx.phase = 0.0; ctx.farad = 0.0; ctx.absorb = 0.0;
         if (alive && !general) {
             March<T> m{st, steps, alive, general};
-            if (VARIANT == 1) {
-                march_generic<T>(grid, C, r, m, s_left0, A.spc, false);
+            if (VARIANT == 1 || AUX) {
+                march_generic<T, AUX>(grid, C, r, m, s_left0, A.spc, false, &ctx);
             } else {
                 if (r.fw != T(0)) march_generic<T>(grid, C, r, m, s_left0, A.spc, true);   // entry through a side face
                 if (alive && !general) {
@@ -540,7 +643,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
                 if (!(left > T(0))) { st |= TT_RAY_TIME_CAP; break; }
                 T ds = ds0 < left ? ds0 : left;
                 Ray<T> old = r;
-                sstep<T>(grid, C, r, ds);
+                AuxCtx<T> old_ctx;
+                if (AUX) old_ctx = ctx;
+                sstep<T, AUX>(grid, C, r, ds, &ctx);
                 ++steps;
                 T lu = leave_fraction(old.iu, old.fu, r.fu, C.nu);
                 T lv = leave_fraction(old.iv, old.fv, r.fv, C.nv);
@@ -549,8 +654,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
                 if (lam <= T(1)) {
                     bool far_face = (lw <= lu && lw <= lv) && r.fw > old.fw;
                     r = old;
+                    if (AUX) ctx = old_ctx;
                     lam = lam < T(0) ? T(0) : lam;
-                    if (lam > T(0)) sstep<T>(grid, C, r, lam * ds);
+                    if (lam > T(0)) sstep<T, AUX>(grid, C, r, lam * ds, &ctx);
                     clamp_in(r.iu, r.fu, C.nu); clamp_in(r.iv, r.fv, C.nv); clamp_in(r.iw, r.fw, C.nw);
                     st |= far_face ? TT_RAY_EXIT_FACE : TT_RAY_EXIT_SIDE;
                     break;
@@ -586,6 +692,11 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
                 sf[(size_t)A.fa[k] * A.np + ray] = Pf[k] + Vf[k] * t_rest;
                 sf[(size_t)(3 + A.fa[k]) * A.np + ray] = Vf[k];
             }
+        }
+        if (AUX) {
+            aux_out[0 * A.np + ray] = exp(-0.5 * ctx.absorb);          // amplitude factor
+            aux_out[1 * A.np + ray] = AX.omega_over_c * ctx.phase;     // phase (rad)
+            aux_out[2 * A.np + ray] = AX.verdet_nc * ctx.farad;        // polarisation rotation (rad)
         }
         if (status) status[ray] = (uint8_t)st;
     }
@@ -914,6 +1025,41 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     else { if (variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
 #undef TT_LAUNCH
     return launch_check("trace_kernel");
+}
+
+extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* grid4_dev,
+                            const void* aux4_dev, const double* s0_dev, long np, const uint32_t* perm_dev,
+                            double* rf_dev, double* sf_dev, double* aux_out_dev, unsigned long long* ray_steps_dev,
+                            uint8_t* status_dev, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(p && a && grid4_dev && s0_dev && rf_dev && aux_out_dev, "tt_trace_aux: null pointer");
+    TT_REQUIRE(np >= 0, "tt_trace_aux: negative ray count");
+    TT_REQUIRE(p->dtype == TT_F32 || p->dtype == TT_F64, "tt_trace_aux: dtype must be TT_F32 or TT_F64");
+    TT_REQUIRE(p->steps_per_cell >= 1 && p->steps_per_cell <= 1024, "tt_trace_aux: steps_per_cell out of range");
+    TT_REQUIRE(p->s_max > 0, "tt_trace_aux: s_max must be > 0");
+    TT_REQUIRE(np < (1L << 32) || !perm_dev, "tt_trace_aux: perm is 32-bit; trace in bundles of < 2^32 rays");
+    TT_REQUIRE(a->omega > 0 && a->nc > 0, "tt_trace_aux: omega and nc must be > 0");
+    TraceArgs A;
+    int rc = fill_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
+    if (rc) return rc;
+    A.extent = p->extent; A.s_max = p->s_max; A.spc = p->steps_per_cell; A.np = np;
+    if (np == 0) return TT_OK;
+    AuxArgs AX;
+    AX.omega_over_c = a->omega / kC;
+    AX.verdet_nc = a->verdet * a->nc;
+    const int block = 128;
+    const long blocks = (np + block - 1) / block;
+    TT_REQUIRE(blocks < (1L << 31), "tt_trace_aux: too many rays for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->dtype == TT_F32)
+        trace_kernel<float, 1, true><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
+                                                                         ray_steps_dev, status_dev, A, 0,
+                                                                         (const float4*)aux4_dev, aux_out_dev, AX);
+    else
+        trace_kernel<double, 1, true><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
+                                                                          ray_steps_dev, status_dev, A, 0,
+                                                                          (const double4*)aux4_dev, aux_out_dev, AX);
+    return launch_check("trace_kernel<aux>");
 }
 
 extern "C" int tt_dndr(const void* grid4_dev, int grid_dtype, const int n_xyz[3], const double origin_xyz[3],

@@ -27,6 +27,9 @@ from ._lib import DeviceArray, TTError
 
 c = 299792458.0                 # scipy.constants.c, particle_tracker.py:119
 _NC_COEFF = 3.14207787e-4       # particle_tracker.py:228
+# Verdet-type constant e^3 / (8 pi^2 eps0 me^2 c^3) (CODATA 2018): rotation = VERDET * lambda^2 * int ne B_par ds
+_E, _EPS0, _ME = 1.602176634e-19, 8.8541878128e-12, 9.1093837015e-31
+VERDET = _E**3 / (8 * np.pi**2 * _EPS0 * _ME**2 * c**3)        # = 2.6312e-13 rad / (T m^2) per m^2 of wavelength^2
 _AXIS = {"x": 0, "y": 1, "z": 2}
 UNIFORM_RTOL = 1e-9
 
@@ -61,13 +64,27 @@ class _GradInterp:
 class ElectronCube:
     """A class to hold and generate electron density cubes (particle_tracker.py:121-145)."""
 
-    def __init__(self, x, y, z, probing_direction="z", *, dtype="float32", steps_per_cell=1,
-                 sort_rays=True, keep_sf=True, verbose=True):
+    def __init__(self, x, y, z, probing_direction="z", *, B_on=False, inv_brems=False, phaseshift=False,
+                 dtype="float32", steps_per_cell=1, sort_rays=True, keep_sf=True, verbose=True):
+        """x, y, z: 1-D coordinate arrays (m); probing_direction 'x' | 'y' | 'z' (:125-145).
+
+        The reference's example scripts call an older signature ``ElectronCube(x, y, z, extent, B_on=,
+        inv_brems=, phaseshift=, probing_direction=)`` (example_kitchensink.py:72): a number in the
+        4th position is accepted as that ``extent`` (it is implied by the axes and only checked)."""
+        if not isinstance(probing_direction, str):
+            raise TypeError("the 4th positional argument must be the probing direction; pass the old-style "
+                            "extent as ElectronCube.legacy(x, y, z, extent, ...)")
         self.z, self.y, self.x = z, y, x
         self.extent_x = x.max()
         self.extent_y = y.max()
         self.extent_z = z.max()
         self.probing_direction = probing_direction
+        # magnetised / absorbing extension (parity unpinned: call sites only in the reference)
+        self.B_on, self.inv_brems, self.phaseshift = bool(B_on), bool(inv_brems), bool(phaseshift)
+        self._B = self._Te = None
+        self._Z = 1.0
+        self._aux = None
+        self.coulomb_log = None
         self.dtype = "float64" if _lib.dtype_code(dtype) == _lib.TT_F64 else "float32"
         self.steps_per_cell = int(steps_per_cell)
         self.sort_rays = bool(sort_rays)
@@ -78,6 +95,11 @@ class ElectronCube:
         self._s0 = None
         self.ray_steps = 0       # RK4 steps taken inside the cube by the last solve()
         self.last_solve_seconds = None
+
+    @classmethod
+    def legacy(cls, x, y, z, extent, **kw):
+        """Old call style of the example scripts: ElectronCube(x, y, z, extent, B_on=..., ...)."""
+        return cls(x, y, z, kw.pop("probing_direction", "z"), **kw)
 
     # ---- geometry -------------------------------------------------------------------------------
     @property
@@ -148,6 +170,69 @@ class ElectronCube:
         shape (len(x), len(y), len(z)), density in m^-3."""
         self._ne = ne.torch if isinstance(ne, DeviceArray) else ne
 
+    def external_B(self, B):
+        """Magnetic field cube, shape (len(x), len(y), len(z), 3), Tesla (example_kitchensink.py:77)."""
+        self._B = B.torch if isinstance(B, DeviceArray) else B
+        self._aux = None
+
+    def external_Te(self, Te):
+        """Electron temperature cube in eV (example_kitchensink.py:75), for inverse bremsstrahlung."""
+        self._Te = Te.torch if isinstance(Te, DeviceArray) else Te
+        self._aux = None
+
+    def external_Z(self, Z):
+        """Ionisation state: scalar or cube (example_kitchensink.py:76)."""
+        self._Z = Z.torch if isinstance(Z, DeviceArray) else Z
+        self._aux = None
+
+    def set_up_interps(self):
+        """Kept for the example scripts (example_kitchensink.py:79): builds the (B, kappa) grid."""
+        self._aux_grid()
+
+    def kappa(self):
+        """Inverse-bremsstrahlung energy absorption coefficient (1/m) on the cube (device tensor),
+        NRL formulary: kappa[cm^-1] = 3.1e-7 Z ne^2 lnL Te^-3/2 omega^-2 (1 - ne/nc)^-1/2 with ne in
+        cm^-3, Te in eV; lnL = max(2, 24 - ln(sqrt(ne)/Te)) unless ``self.coulomb_log`` is set."""
+        torch = _lib.torch_cuda()
+        if self._Te is None:
+            raise AttributeError("inv_brems=True needs external_Te(Te)")
+        ne = _lib.to_device(self._ne, torch.float64)
+        Te = _lib.to_device(self._Te, torch.float64).expand(*self.shape)
+        Z = self._Z if isinstance(self._Z, (int, float)) else _lib.to_device(self._Z, torch.float64)
+        ne_cc = ne * 1e-6
+        if self.coulomb_log is None:
+            lnL = torch.clamp(24.0 - torch.log(torch.sqrt(torch.clamp(ne_cc, min=1e-30)) / Te), min=2.0)
+        else:
+            lnL = float(self.coulomb_log)
+        ne_nc = torch.clamp(ne / self.nc, max=float(self.ne_max))
+        disp = torch.sqrt(torch.clamp(1.0 - ne_nc, min=1e-6))
+        return 100.0 * 3.1e-7 * Z * ne_cc**2 * lnL * Te**-1.5 / (self.omega**2 * disp)
+
+    def _aux_grid(self):
+        """(B_u, B_v, B_w, kappa) in the layout/dtype of the gradient grid, or None (phase only)."""
+        torch = _lib.torch_cuda()
+        if not (self.B_on or self.inv_brems):
+            return None
+        if self._aux is not None:
+            return self._aux
+        grid = self._require_grid()
+        fa = self._frame
+        comps = []
+        if self.B_on:
+            if self._B is None:
+                raise AttributeError("B_on=True needs external_B(B)")
+            B = _lib.to_device(self._B, torch.float64)
+            if tuple(B.shape) != self.shape + (3,):
+                raise ValueError(f"B has shape {tuple(B.shape)}, expected {self.shape + (3,)}")
+            comps = [B[..., fa[0]], B[..., fa[1]], B[..., fa[2]]]
+        else:
+            z = torch.zeros(self.shape, dtype=torch.float64, device="cuda")
+            comps = [z, z, z]
+        comps.append(self.kappa() if self.inv_brems else torch.zeros(self.shape, dtype=torch.float64, device="cuda"))
+        a = torch.stack(comps, dim=-1).permute(fa[2], fa[1], fa[0], 3).to(grid.dtype).contiguous()
+        self._aux = a
+        return a
+
     @property
     def ne(self):
         if self._ne is None:
@@ -173,6 +258,8 @@ class ElectronCube:
         self.omega = 2 * np.pi * (c / lwl)
         self.nc = _NC_COEFF * self.omega**2
         self.ne_max = ne_max
+        self.VerdetConst = VERDET * lwl**2          # rad / (T m^2)
+        self._aux = None
         origin, spacing = self._geometry()
         ne = self._ne
         if tuple(ne.shape) != self.shape:
@@ -285,8 +372,11 @@ class ElectronCube:
         if not hasattr(self, "extent"):
             self.extent = (self.extent_x, self.extent_y, self.extent_z)[self._par]
         s0 = _lib.to_device(self._s0, torch.float64)
-        if s0.dim() != 2 or s0.shape[0] != 6:
-            raise ValueError("s0 must have shape (6, Np)")
+        if s0.dim() != 2 or s0.shape[0] not in (6, 9):
+            raise ValueError("s0 must have shape (6, Np) (or (9, Np) with amplitude, phase, polarisation rows)")
+        init_aux = s0[6:9] if s0.shape[0] == 9 else None
+        s0 = s0[:6].contiguous()
+        use_aux = self.B_on or self.inv_brems or self.phaseshift
         Np = s0.shape[1]
         if Np == 0:                                   # empty bundle: nothing to launch
             self.rf = DeviceArray(torch.empty((4, 0), dtype=torch.float64, device="cuda"))
@@ -324,8 +414,25 @@ class ElectronCube:
         if events is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0), Np, _lib.ptr(perm), _lib.ptr(rf),
-                                _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
+        if use_aux:
+            ap = _lib.AuxParams(float(self.omega), float(self.nc), float(self.VerdetConst))
+            aux4 = self._aux_grid()
+            aux_out = torch.empty((3, Np), dtype=torch.float64, device="cuda")
+            _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0), Np,
+                                        _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out), _lib.ptr(steps),
+                                        _lib.ptr(status), stream), "tt_trace_aux")
+            if not self.phaseshift:
+                aux_out[1].zero_()
+            if init_aux is not None:       # rows 6-8 of a 9-row s0: initial amplitude, phase, polarisation
+                aux_out[0] *= init_aux[0]
+                aux_out[1] += init_aux[1]
+                aux_out[2] += init_aux[2]
+            self.amp, self.phase, self.pol = (DeviceArray(aux_out[i]) for i in range(3))
+            self._aux_out = aux_out
+        else:
+            self._aux_out = None
+            _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0), Np, _lib.ptr(perm), _lib.ptr(rf),
+                                    _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
         if events is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
@@ -350,6 +457,18 @@ class ElectronCube:
     @ray_steps.setter
     def ray_steps(self, v):
         self._steps_dev = None
+
+    @property
+    def Jf(self):
+        """Jones vector (2 x Np complex: E_x, E_y) at the exit, as used by example_kitchensink.py:92-101:
+        amplitude * exp(i phase) * (sin(pol), cos(pol)) -- the beam starts polarised along E_y, so
+        atan(E_x/E_y) is the Faraday rotation."""
+        a = getattr(self, "_aux_out", None)
+        if a is None:
+            raise AttributeError("Jf needs B_on, inv_brems or phaseshift and a solve()")
+        amp, ph, pol = (t.cpu().numpy() for t in a)
+        e = amp * np.exp(1j * ph)
+        return np.stack([e * np.sin(pol), e * np.cos(pol)])
 
     def trace_ms(self):
         """Durations (ms) of the trace-kernel launches recorded since ``_trace_events = []`` was set;

@@ -20,7 +20,7 @@ from ._lib import DeviceArray
 
 __all__ = ["m_to_mm", "lens", "sym_lens", "distance", "circular_aperture", "circular_stop", "annular_stop",
            "angular_filter", "rect_aperture", "knife_edge", "plot_afr", "Rays", "Shadowgraphy", "Schlieren_DF",
-           "Schlieren_LF", "AFR"]
+           "Schlieren_LF", "AFR", "Refractometer", "ShadowgraphyRays", "SchlierenRays", "BurdiscopeRays"]
 
 
 # ---- element programs ---------------------------------------------------------------------------
@@ -324,3 +324,31 @@ class AFR(Rays):
             _op_distance(L / 4), *_ops_angular_filter(Rs),
             _op_distance(L / 4), _op(_lib.OP_CIRC_APERTURE, Ra), _op_lens(L / 2, L / 2),
             _op_distance(L / 2)])
+
+
+class Refractometer(Rays):
+    """Imaging refractometer ("Burdiscope"): the detector shows POSITION along x and ray ANGLE along y.
+
+    PARITY UNPINNED: the reference checkout only has call sites (``rtm.BurdiscopeRays(rf)``,
+    example_MPI.py:67-69, example_multiprocess.py:65) and the building block ``lens(r, f1, f2)`` with
+    independent focal lengths (ray_transfer_matrix.py:42-54); this program is composed here from those
+    elements.  A 4f relay (as Shadowgraphy) forms an image at L behind lens 2; a hybrid (cylindrical)
+    lens L/2 further on with f_x = L/3, f_y = L images that plane onto the detector in x
+    (magnification -2: x_det = 2 x0 - ...) and puts the detector in its focal plane in y
+    (y_det = -L * phi0), L behind it.  Apertures of radius R at the relay lenses, a rectangular
+    aperture (R, R) at the hybrid lens."""
+
+    def solve(self):
+        L, R = self.L, self.R
+        self._set_program([
+            _op_distance(L - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, R), _op_lens(L, L),
+            _op_distance(L * 2),
+            _op(_lib.OP_CIRC_APERTURE, R), _op_lens(L, L),
+            _op_distance(L + L / 2), _op(_lib.OP_RECT_APERTURE, R, R), _op_lens(L / 3, L),
+            _op_distance(L)])
+
+
+# names used by the reference's (stale) example scripts: example_MPI.py:67-77, example_multiprocess.py:65-67
+ShadowgraphyRays = Shadowgraphy
+SchlierenRays = Schlieren_DF
+BurdiscopeRays = Refractometer
