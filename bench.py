@@ -247,15 +247,29 @@ def run_gpu_arm(args, wl):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     trace_ms = []
 
+    phase_events = []          # per step: events at the phase boundaries (read after the timed region)
+
+    def mark(lst):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        lst.append(e)
+
     def step_device():
+        marks = []
+        mark(marks)
         cube.external_ne(ne)
         cube.calc_dndr(LWL)
+        mark(marks)
         cube.s0 = s0_dev
         rf = cube.solve()
+        mark(marks)
         sh = rtm.Shadowgraphy(rf)
         sh.solve()
         sh.histogram(to_host=False)
+        mark(marks)
         H = ttd.allreduce_histograms([sh.H_dev])[0]
+        mark(marks)
+        phase_events.append(marks)
         return H, cube._steps_dev
 
     def timed(fn, c, warmup, steps, sampler=None):
@@ -286,6 +300,9 @@ def run_gpu_arm(args, wl):
 
     ms, tot_steps, last, clocks = timed(step_device, cube, args.warmup, args.steps, ClockSampler(local))
     kernel_ms = float(np.mean(trace_ms)) if trace_ms else float("nan")
+    names = ["calc_dndr", "sort+trace", "optics+hist", "allreduce"]
+    phases = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in phase_events[-args.steps:]]))
+              for i, n in enumerate(names)}
     steps_per_launch = tot_steps / (args.steps * world)
     value = tot_steps / (ms * 1e-3)
     H_dev = last[0]
@@ -362,7 +379,7 @@ def run_gpu_arm(args, wl):
                        "cube_setup_s": t_cube, "kernel_variant": args.variant},
             "e2e": e2e, "gpu_launches": 4 * args.steps,
             "gpu_launches_note": "per step: calc_dndr, morton_key, trace, optics_hist (+ CUB radix-sort passes)",
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "phases_ms_rank0": phases,
             "histogram_sum": int(H_dev.sum().item()),
         }
         print(json.dumps(line), flush=True)

@@ -167,6 +167,15 @@ int tt_optics_hist_perm(const double* rf_in_dev, long np, const uint32_t* perm_d
                         const double* yedges_dev, int nby, unsigned long long* H_dev,
                         double* rf_out_dev, tt_stream_t stream);
 
+/* same, plus a weighted image Hw_dev[nby][nbx] (double) += weights_dev[ray], i.e.
+ * numpy.histogram2d(..., weights=w) as example_kitchensink.py:108-129 uses for amplitude- and
+ * polarisation-weighted images.  H_dev may be NULL when only the weighted image is wanted.        */
+int tt_optics_hist_weighted(const double* rf_in_dev, long np, const uint32_t* perm_dev, double pos_scale,
+                            const tt_optic* program, int n_ops, const double* xedges_dev, int nbx,
+                            const double* yedges_dev, int nby, unsigned long long* H_dev,
+                            const double* weights_dev, double* Hw_dev, double* rf_out_dev,
+                            tt_stream_t stream);
+
 /* ---- K7: turboGen.gaussian3D_FFT (gaussian_fields/turboGen.py:488-538) -----------------------
  * Hermitian spectrum shaping + inverse real FFT (cuFFT) on the odd grid M = 2N+1.
  * sqrtP_lut_dev[3N^2+1]: sqrt(k_func(sqrt(q)/M)) for q = i^2+j^2+l^2 (the host evaluates the

@@ -161,6 +161,32 @@ def golden_traces():
     save("trace_liner", n=31, s0=cube.s0, rf=rf, sf=sf, extent=cube.extent)
 
 
+# ---------------------------------------------------------------- BASELINE configs[0] (C1), reduced ray count
+def golden_c1():
+    """100^3 test_exponential_cos cube (parameters of example_multiprocess.py:35-38), beam 4 mm,
+    divergence 0.05 mrad, seed 0; 1024 rays traced by the reference at rtol 1e-10, then the
+    reference's own detectors and histograms on those rays."""
+    x = axes(100)
+    cube = pt.ElectronCube(x, x, x)
+    cube.test_exponential_cos(n_e0=2e23, Ly=1e-3, s=4e-3)
+    cube.calc_dndr()
+    np.random.seed(0)
+    cube.init_beam(1024, 4e-3, 0.05e-3)
+    rf, sf = tight_trace(cube, 1e-10, 1e-13, 32)
+    out = dict(s0=cube.s0, rf=rf, sf=sf)
+    dets = {"sh": (rtm.Shadowgraphy, {}), "df": (rtm.Schlieren_DF, dict(R=1)), "lf": (rtm.Schlieren_LF, dict(R=1)),
+            "afr": (rtm.AFR, dict(Rs=np.arange(0, 6, .5)))}
+    for k, (cls, skw) in dets.items():
+        d = cls(rf)
+        d.solve(**skw)
+        d.histogram(bin_scale=10)
+        iy, ix = np.nonzero(d.H)
+        out[k + "_idx"] = np.stack([iy, ix]).astype(np.int32)
+        out[k + "_cnt"] = d.H[iy, ix].astype(np.int32)
+        out[k + "_rf"] = d.rf
+    save("c1_expcos100", **out)
+
+
 # ---------------------------------------------------------------- optics + histogram
 def golden_optics():
     rng = np.random.RandomState(21)
@@ -217,8 +243,12 @@ def golden_grf():
 
 
 if __name__ == "__main__":
+    if "--c1" in sys.argv:
+        golden_c1()
+        sys.exit(0)
     golden_calc_dndr()
     golden_init_beam()
     golden_optics()
     golden_grf()
     golden_traces()
+    golden_c1()

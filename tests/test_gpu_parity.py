@@ -708,3 +708,60 @@ def test_refractometer_images_position_in_x_and_angle_in_y(tt):
     d.histogram(bin_scale=10)
     assert d.H.sum() == np.sum(ok & (np.abs(rf[0]) <= 9) & (np.abs(rf[2]) <= 6.75))
     assert rtm.ShadowgraphyRays is rtm.Shadowgraphy and rtm.SchlierenRays is rtm.Schlieren_DF
+
+
+def test_weighted_histogram_matches_numpy(tt, golden):
+    """amplitude-weighted detector image, numpy.histogram2d(weights=) as example_kitchensink.py:108"""
+    rtm = tt.ray_transfer_matrix
+    g = golden("optics")
+    r0 = g["r0"]
+    w = np.random.RandomState(0).rand(r0.shape[1])
+    d = rtm.Shadowgraphy(r0, Lx=6, Ly=6)
+    d.solve()
+    d.histogram(bin_scale=25, weights=w)
+    rf = g["sh_rf"]
+    ok = ~np.isnan(rf[0])
+    Hw, _, _ = np.histogram2d(rf[0][ok], rf[2][ok], bins=[3448 // 25, 2574 // 25], range=[[-3, 3], [-3, 3]], weights=w[ok])
+    np.testing.assert_allclose(d.Hw, Hw.T, rtol=1e-12, atol=1e-13)
+    H, _, _ = orc.histogram(rf, Lx=6, Ly=6, bin_scale=25)
+    np.testing.assert_array_equal(d.H, H)
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs[0]
+@pytest.mark.parametrize("dtype,spc", [("float32", 1), ("float64", 2)])
+def test_c1_end_to_end_against_reference(tt, golden, dtype, spc):
+    """configs[0]: 100^3 test_exponential_cos cube, seed-0 beam, the four detectors -- the whole chain
+    (device test_* set-up, calc_dndr, solve, detectors, histograms) against the reference's own output
+    for the same 1024 rays.  Histogram bound: L1(H - H_ref) / sum(H_ref) <= 2/1024 per detector
+    (identical rays up to ~1e-9 m: only a ray sitting on a bin or aperture edge may move)."""
+    pt, rtm = tt.particle_tracker, tt.ray_transfer_matrix
+    g = golden("c1_expcos100")
+    x = np.linspace(-5e-3, 5e-3, 100)
+    cube = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=spc, verbose=False)
+    cube.test_exponential_cos(n_e0=2e23, Ly=1e-3, s=4e-3)
+    np.testing.assert_allclose(cube.ne, orc.density("exponential_cos", x, x, x, n_e0=2e23, Ly=1e-3, s=4e-3), rtol=1e-12)
+    cube.calc_dndr()
+    np.random.seed(0)
+    cube.init_beam(1024, 4e-3, 0.05e-3)
+    np.testing.assert_array_equal(cube.s0, g["s0"])
+    rf = cube.solve()
+    pos, ang = _errors(np.asarray(rf), g["rf"], g["s0"], 2)
+    print(f"C1 {dtype} spc={spc}: pos err {pos:.2e} m ({pos / PIXEL_M:.1e} pixel), angle err {ang:.1e} of rms")
+    assert pos <= (1e-3 * PIXEL_M if dtype == "float32" else 1e-5 * 4e-3)
+    assert ang <= (1e-4 if dtype == "float32" else 1e-5)
+    dets = {"sh": (rtm.Shadowgraphy, {}), "df": (rtm.Schlieren_DF, dict(R=1)), "lf": (rtm.Schlieren_LF, dict(R=1)),
+            "afr": (rtm.AFR, dict(Rs=np.arange(0, 6, .5)))}
+    for k, (cls, skw) in dets.items():
+        d = cls(rf)
+        d.solve(**skw)
+        d.histogram(bin_scale=10)
+        Href = np.zeros((257, 344))
+        Href[g[k + "_idx"][0], g[k + "_idx"][1]] = g[k + "_cnt"]
+        l1 = np.abs(d.H - Href).sum() / max(Href.sum(), 1)
+        print(f"   {k}: accepted {int(d.H.sum())} / ref {int(Href.sum())}, L1 = {l1:.2e}")
+        assert l1 <= 2 / 1024
+        ok = ~np.isnan(g[k + "_rf"][0])
+        mine = np.asarray(d.rf)
+        assert np.mean(np.isnan(mine[0]) == ~ok) > 0.998
+        both = ok & ~np.isnan(mine[0])
+        np.testing.assert_allclose(mine[0][both], g[k + "_rf"][0][both], rtol=0, atol=1e-3 * PIXEL_M * 1e3)

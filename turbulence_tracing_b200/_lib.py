@@ -66,6 +66,7 @@ PROTOTYPES = {
                           _vp, _vp]),
     "tt_optics_hist": (_i, [_vp, _l, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_optics_hist_perm": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "tt_optics_hist_weighted": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "tt_grf_workspace": (_i, [_i, _i, C.POINTER(_sz)]),
     "tt_grf3d": (_i, [_i, _i, _vp, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
     "tt_grf_nd_workspace": (_i, [_i, _i, _i, C.POINTER(_sz)]),

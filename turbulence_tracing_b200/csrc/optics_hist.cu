@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __r
                                                                const double* __restrict__ xe,
                                                                const double* __restrict__ ye,
                                                                unsigned long long* __restrict__ H,
-                                                               double* __restrict__ rf_out, OpticsArgs A) {
+                                                               double* __restrict__ rf_out, OpticsArgs A,
+                                                               const double* __restrict__ weights,
+                                                               double* __restrict__ Hw) {
     __shared__ unsigned tile[kTile * kTile];
     __shared__ int anchor[2];
     for (int i = threadIdx.x; i < kTile * kTile; i += kThreads) tile[i] = 0u;
@@ -109,16 +111,18 @@ __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __r
             if (rf_out) {
                 rf_out[ray] = x; rf_out[A.np + ray] = th; rf_out[2 * A.np + ray] = y; rf_out[3 * A.np + ray] = ph;
             }
-            if (H) {
+            if (H || Hw) {
                 const int ix = bin_of(x, xe, A.nbx), iy = bin_of(y, ye, A.nby);
                 if (ix >= 0 && iy >= 0) {
                     bx[k] = ix; by[k] = iy;
                     mnx = min(mnx, ix); mny = min(mny, iy);
+                    // weighted image (numpy.histogram2d(weights=)): FP64 atomics straight to global
+                    if (Hw) atomicAdd(&Hw[(size_t)iy * A.nbx + ix], weights[ray]);
                 }
             }
         }
     }
-    if (!H) return;
+    if (!H) return;      // (uniform) rf only, or weighted image only
     // CTA-wide anchor = smallest occupied bin in x and y
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -144,17 +148,19 @@ __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __r
 
 }  // namespace tt
 
-extern "C" int tt_optics_hist_perm(const double* rf_in_dev, long np, const uint32_t* perm_dev, double pos_scale,
-                                   const tt_optic* program, int n_ops, const double* xedges_dev, int nbx,
-                                   const double* yedges_dev, int nby, unsigned long long* H_dev,
-                                   double* rf_out_dev, tt_stream_t stream) {
+extern "C" int tt_optics_hist_weighted(const double* rf_in_dev, long np, const uint32_t* perm_dev, double pos_scale,
+                                       const tt_optic* program, int n_ops, const double* xedges_dev, int nbx,
+                                       const double* yedges_dev, int nby, unsigned long long* H_dev,
+                                       const double* weights_dev, double* Hw_dev, double* rf_out_dev,
+                                       tt_stream_t stream) {
     using namespace tt;
     TT_REQUIRE(rf_in_dev, "tt_optics_hist: null rf_in");
+    TT_REQUIRE((weights_dev == nullptr) == (Hw_dev == nullptr), "tt_optics_hist: weights and Hw go together");
     TT_REQUIRE(np >= 0, "tt_optics_hist: negative ray count");
     TT_REQUIRE(n_ops >= 0 && n_ops <= TT_MAX_OPTICS, "tt_optics_hist: program length %d exceeds TT_MAX_OPTICS", n_ops);
     TT_REQUIRE(n_ops == 0 || program, "tt_optics_hist: null program");
-    TT_REQUIRE(H_dev || rf_out_dev, "tt_optics_hist: nothing to compute (H and rf_out both null)");
-    if (H_dev) TT_REQUIRE(xedges_dev && yedges_dev && nbx >= 1 && nby >= 1, "tt_optics_hist: histogram needs edges and bin counts >= 1");
+    TT_REQUIRE(H_dev || rf_out_dev || Hw_dev, "tt_optics_hist: nothing to compute (H, Hw and rf_out all null)");
+    if (H_dev || Hw_dev) TT_REQUIRE(xedges_dev && yedges_dev && nbx >= 1 && nby >= 1, "tt_optics_hist: histogram needs edges and bin counts >= 1");
     OpticsArgs A;
     for (int i = 0; i < n_ops; ++i) {
         A.ops[i] = program[i];
@@ -169,8 +175,17 @@ extern "C" int tt_optics_hist_perm(const double* rf_in_dev, long np, const uint3
     const long blocks = (np + per - 1) / per;
     TT_REQUIRE(blocks < (1L << 31), "tt_optics_hist: too many rays for one launch");
     optics_hist_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(rf_in_dev, perm_dev, xedges_dev,
-                                                                                yedges_dev, H_dev, rf_out_dev, A);
+                                                                                yedges_dev, H_dev, rf_out_dev, A,
+                                                                                weights_dev, Hw_dev);
     return launch_check("optics_hist_kernel");
+}
+
+extern "C" int tt_optics_hist_perm(const double* rf_in_dev, long np, const uint32_t* perm_dev, double pos_scale,
+                                   const tt_optic* program, int n_ops, const double* xedges_dev, int nbx,
+                                   const double* yedges_dev, int nby, unsigned long long* H_dev,
+                                   double* rf_out_dev, tt_stream_t stream) {
+    return tt_optics_hist_weighted(rf_in_dev, np, perm_dev, pos_scale, program, n_ops, xedges_dev, nbx, yedges_dev, nby,
+                                   H_dev, nullptr, nullptr, rf_out_dev, stream);
 }
 
 extern "C" int tt_optics_hist(const double* rf_in_dev, long np, double pos_scale, const tt_optic* program, int n_ops,

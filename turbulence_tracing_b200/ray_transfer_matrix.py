@@ -49,8 +49,9 @@ def _ops_angular_filter(Rs):
     return [_op(_lib.OP_ANNULAR_STOP, Rs[2 * i], Rs[2 * i + 1]) for i in range(len(Rs) // 2)]
 
 
-def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True):
-    """Launch the fused kernel.  hist = (xedges_dev, yedges_dev, H_dev) or None."""
+def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True, weights=None, Hw=None):
+    """Launch the fused kernel.  hist = (xedges_dev, yedges_dev, H_dev) or None; weights/Hw: optional
+    per-ray weights and the FP64 image they are summed into."""
     torch = _lib.torch_cuda()
     lib = _lib.load()
     if r_dev.dim() != 2 or r_dev.shape[0] != 4:
@@ -67,9 +68,9 @@ def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True):
     if hist is not None:
         xe, ye, H = hist
         nbx, nby = xe.numel() - 1, ye.numel() - 1
-    _lib.check(lib.tt_optics_hist_perm(_lib.ptr(r_dev), n, _lib.ptr(perm), float(pos_scale), prog, len(program),
-                                       _lib.ptr(xe), nbx, _lib.ptr(ye), nby, _lib.ptr(H), _lib.ptr(out),
-                                       _lib.stream_ptr()), "tt_optics_hist")
+    _lib.check(lib.tt_optics_hist_weighted(_lib.ptr(r_dev), n, _lib.ptr(perm), float(pos_scale), prog, len(program),
+                                           _lib.ptr(xe), nbx, _lib.ptr(ye), nby, _lib.ptr(H), _lib.ptr(weights),
+                                           _lib.ptr(Hw), _lib.ptr(out), _lib.stream_ptr()), "tt_optics_hist")
     return out
 
 
@@ -226,11 +227,14 @@ class Rays:
         if v is None:
             self._program = None
 
-    def histogram(self, bin_scale=10, pix_x=3448, pix_y=2574, clear_mem=False, to_host=True):
+    def histogram(self, bin_scale=10, pix_x=3448, pix_y=2574, clear_mem=False, to_host=True, weights=None):
         """Bin detector-plane rays; defaults are for a KAF-8300 (:173-195).  Sets ``H``
         (pix_y//bin_scale, pix_x//bin_scale) float64 like numpy.histogram2d(...).T, ``xedges``,
         ``yedges``; ``H_dev`` keeps the integer counts on the device (for NCCL all-reduce).
-        ``to_host=False`` skips the device->host copy of H (multi-GPU drivers reduce H_dev first)."""
+        ``to_host=False`` skips the device->host copy of H (multi-GPU drivers reduce H_dev first).
+        ``weights`` (N,): additionally sums the weights of the binned rays into ``Hw`` / ``Hw_dev`` (FP64),
+        like ``numpy.histogram2d(..., weights=)`` in example_kitchensink.py:108-129 (amplitude- or
+        polarisation-weighted images; the weights refer to the rays in their original order)."""
         torch = _lib.torch_cuda()
         nbx, nby = pix_x // bin_scale, pix_y // bin_scale
         # numpy.histogramdd builds its edges with linspace(range_min, range_max, bins + 1)
@@ -239,14 +243,25 @@ class Rays:
         xe = torch.from_numpy(self.xedges).cuda()
         ye = torch.from_numpy(self.yedges).cuda()
         H = torch.zeros((nby, nbx), dtype=torch.int64, device="cuda")
+        w = Hw = None
+        if weights is not None:
+            w = _lib.to_device(weights, torch.float64).reshape(-1)
+            Hw = torch.zeros((nby, nbx), dtype=torch.float64, device="cuda")
         if self._rf is not None:                      # rays already at the detector plane
-            _run(self._rf.torch, [], perm=self._perm, hist=(xe, ye, H), want_rf=False)
+            if w is not None and w.numel() != self._rf.torch.shape[1]:
+                raise ValueError("weights must have one entry per ray")
+            _run(self._rf.torch, [], perm=self._perm, hist=(xe, ye, H), want_rf=False, weights=w, Hw=Hw)
         elif self._program is not None and self._r0_m is not None:   # fused: optics + binning, one pass
-            _run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm, hist=(xe, ye, H), want_rf=False)
+            if w is not None and w.numel() != self._r0_m.shape[1]:
+                raise ValueError("weights must have one entry per ray")
+            _run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm, hist=(xe, ye, H), want_rf=False,
+                 weights=w, Hw=Hw)
         else:
             raise AttributeError("no rays to bin: call solve() first")
         self.H_dev = H
         self.H = H.double().cpu().numpy() if to_host else None
+        self.Hw_dev = Hw
+        self.Hw = Hw.cpu().numpy() if (Hw is not None and to_host) else None
         if clear_mem:
             self.clear_rays()
 
