@@ -105,7 +105,8 @@ typedef struct tt_trace_params {
     int steps_per_cell;     /* >= 1                                          */
     int dtype;              /* TT_F32 or TT_F64: grid element type and state arithmetic */
     int variant;            /* 0 = auto (event marching if status_dev is given, else cell cache);
-                               1 = 8-corner gather per stage; 2 = cell cache; 3 = event marching */
+                               1 = 8-corner gather per stage; 2 = cell cache; 3 = event marching
+                               (packed FP32x2 arithmetic in TT_F32); 4 = event marching, scalar     */
 } tt_trace_params;
 
 int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_dev, long np,

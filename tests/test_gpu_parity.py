@@ -193,7 +193,7 @@ def test_kernel_variants_agree(tt, golden, dtype, spc):
     g = golden("trace_grf33")
     pt = tt.particle_tracker
     out = {}
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         cube = pt.ElectronCube(g["x"], g["x"], g["x"], dtype=dtype, steps_per_cell=spc, verbose=False)
         cube.kernel_variant = variant
         cube.external_ne(g["ne"])
@@ -221,6 +221,10 @@ def test_kernel_variants_agree(tt, golden, dtype, spc):
     assert np.abs(a[0] - b[0]).max() <= ptol and np.abs(a[2] - b[2]).max() <= ptol
     assert np.abs(a[1] - b[1]).max() <= atol and np.abs(a[3] - b[3]).max() <= atol
     np.testing.assert_allclose(fa[:3], fb[:3], rtol=0, atol=10 * ptol)
+    # 4 (scalar arithmetic) vs 3 (packed FP32x2 in float32; the same kernel in float64): identical bits
+    np.testing.assert_array_equal(out[4][0], out[3][0])
+    np.testing.assert_array_equal(out[4][3], out[3][3])
+    assert out[4][2] == out[3][2]
     # 3 vs converged: at least as accurate as 1 (plus the rounding floor of the arithmetic)
     (a, sa, na, fa) = out[3]
     e3 = err(a)

@@ -17,17 +17,21 @@ template <> struct Vec4<double> { typedef double4 type; };
 
 struct DndrArgs {
     int n[3];          // nx, ny, nz
-    double inv2h[3];   // unused placeholder kept for alignment
-    double h[3];       // spacing per axis (x, y, z)
+    double inv2h[3];   // 1 / (2 h) per axis (central differences)
+    double invh[3];    // 1 / h per axis (one-sided differences on the faces)
+    double inv_nc;     // 1 / nc
     int fa[3];         // frame: (u, v, w) -> xyz axis
     double nc, ne_max;
     int third;         // the xyz axis that is neither z nor the u axis
 };
 
+// ne/nc clipped at ne_max.  Multiplying by 1/nc instead of dividing differs from the reference's
+// quotient by at most 1 ulp and keeps the kernel bandwidth-bound (an FP64 division costs ~30 instructions
+// and this is evaluated for the voxel and its 6 neighbours).
 template <typename TIn>
-__device__ __forceinline__ double ne_over_nc(const TIn* __restrict__ ne, size_t idx, double nc,
+__device__ __forceinline__ double ne_over_nc(const TIn* __restrict__ ne, size_t idx, double inv_nc,
                                              double ne_max) {
-    double v = (double)ne[idx] / nc;     // particle_tracker.py:230
+    double v = (double)ne[idx] * inv_nc; // particle_tracker.py:230
     return v > ne_max ? ne_max : v;      // :231 (NaN stays NaN, as with numpy's mask)
 }
 
@@ -35,13 +39,12 @@ __device__ __forceinline__ double ne_over_nc(const TIn* __restrict__ ne, size_t 
 // (edge_order=1, numpy/lib/_function_base_impl.py:1294-1334), uniform spacing h.
 template <typename TIn>
 __device__ __forceinline__ double axis_gradient(const TIn* __restrict__ ne, size_t idx, size_t stride,
-                                                int i, int n, double h, double centre, double nc,
-                                                double ne_max) {
+                                                int i, int n, double invh, double inv2h, double centre,
+                                                double nc, double ne_max) {
     if (n == 1) return 0.0;
-    if (i == 0) return (ne_over_nc(ne, idx + stride, nc, ne_max) - centre) / h;
-    if (i == n - 1) return (centre - ne_over_nc(ne, idx - stride, nc, ne_max)) / h;
-    return (ne_over_nc(ne, idx + stride, nc, ne_max) - ne_over_nc(ne, idx - stride, nc, ne_max)) /
-           (2.0 * h);
+    if (i == 0) return (ne_over_nc(ne, idx + stride, nc, ne_max) - centre) * invh;
+    if (i == n - 1) return (centre - ne_over_nc(ne, idx - stride, nc, ne_max)) * invh;
+    return (ne_over_nc(ne, idx + stride, nc, ne_max) - ne_over_nc(ne, idx - stride, nc, ne_max)) * inv2h;
 }
 
 template <typename TIn, typename TOut, int PAR>
@@ -67,11 +70,11 @@ __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ 
             int i3[3];
             i3[2] = iz; i3[ua] = iu; i3[ta] = t;
             const size_t idx = (size_t)i3[0] * sx + (size_t)i3[1] * sy + i3[2];
-            const double c = ne_over_nc(ne, idx, a.nc, a.ne_max);
+            const double c = ne_over_nc(ne, idx, a.inv_nc, a.ne_max);
             double g[3];
-            g[0] = -0.5 * axis_gradient(ne, idx, sx, i3[0], nx, a.h[0], c, a.nc, a.ne_max);
-            g[1] = -0.5 * axis_gradient(ne, idx, sy, i3[1], ny, a.h[1], c, a.nc, a.ne_max);
-            g[2] = -0.5 * axis_gradient(ne, idx, 1, i3[2], nz, a.h[2], c, a.nc, a.ne_max);
+            g[0] = -0.5 * axis_gradient(ne, idx, sx, i3[0], nx, a.invh[0], a.inv2h[0], c, a.inv_nc, a.ne_max);
+            g[1] = -0.5 * axis_gradient(ne, idx, sy, i3[1], ny, a.invh[1], a.inv2h[1], c, a.inv_nc, a.ne_max);
+            g[2] = -0.5 * axis_gradient(ne, idx, 1, i3[2], nz, a.invh[2], a.inv2h[2], c, a.inv_nc, a.ne_max);
             V4 o;
             o.x = (TOut)g[F0]; o.y = (TOut)g[F1]; o.z = (TOut)g[F2]; o.w = (TOut)c;
             tile[r + threadIdx.y][threadIdx.x] = o;
@@ -120,8 +123,8 @@ extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3]
         TT_REQUIRE(n_xyz[i] >= 2, "tt_calc_dndr: every axis needs >= 2 points (axis %d has %d)", i, n_xyz[i]);
         TT_REQUIRE(spacing_xyz[i] > 0, "tt_calc_dndr: spacing must be > 0");
         a.n[i] = n_xyz[i];
-        a.h[i] = spacing_xyz[i];
-        a.inv2h[i] = 0;
+        a.invh[i] = 1.0 / spacing_xyz[i];
+        a.inv2h[i] = 1.0 / (2.0 * spacing_xyz[i]);
     }
     TT_REQUIRE(n_xyz[0] <= 65535 * 32 && n_xyz[1] <= 65535 * 32, "tt_calc_dndr: cube too large");
     TT_REQUIRE(nc > 0, "tt_calc_dndr: critical density must be > 0");
@@ -129,6 +132,7 @@ extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3]
     for (int i = 0; i < 3; ++i) a.fa[i] = f.a[i];
     a.third = 3 - 2 - a.fa[0];   // axes are {0,1,2}; z = 2 and u = fa[0] are taken
     a.nc = nc;
+    a.inv_nc = 1.0 / nc;
     a.ne_max = ne_max;
     TT_REQUIRE(a.n[a.third] <= 65535, "tt_calc_dndr: axis too long for grid.z");
     cudaStream_t s = (cudaStream_t)stream;

@@ -929,6 +929,221 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
     }
 }
 
+// ---- variant 3 in FP32: the same event-marching kernel written with Blackwell's packed FP32x2 math ----
+// sm_100 executes two FP32 FMAs per instruction on a 64-bit register pair (SASS FFMA2 / FADD2 / FMUL2,
+// PTX fma.rn.f32x2, with a scalar-broadcast operand form).  The FP32 lanes are not faster, but the
+// kernel is bound by instruction ISSUE (profiles/: issue slots 75 %, FMA pipe 57 %), so halving the
+// instruction count of the FP work pays.  Pairs: the (u, v) fractions, the (u, v) direction
+// components, and the float4 grid lanes as (g_u, g_v) and (g_w, ne/nc) -- the 4th lane rides along for
+// free.  Every lane performs exactly the operations of the scalar kernel above, in the same order, so
+// the two produce bit-identical rays (tested).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+struct Tri2 {          // two trilinear polynomials (one per lane) of one cell
+    f32x2 a, b, c, d, a1, b1, c1, d1;
+};
+__device__ __forceinline__ f32x2 tri2_eval(const Tri2& q, f32x2 TU, f32x2 TV, f32x2 FW) {
+    f32x2 lo = fma2(TV, fma2(TU, q.d, q.c), fma2(TU, q.b, q.a));
+    f32x2 hi = fma2(TV, fma2(TU, q.d1, q.c1), fma2(TU, q.b1, q.a1));
+    return fma2(FW, hi, lo);
+}
+__device__ __forceinline__ void tri2_set(Tri2& q, f32x2 c00, f32x2 c10, f32x2 c01, f32x2 c11, f32x2 e00, f32x2 e10,
+                                         f32x2 e01, f32x2 e11) {
+    q.a = c00; q.b = sub2(c10, c00); q.c = sub2(c01, c00); q.d = sub2(sub2(c11, c01), q.b);
+    f32x2 eb = sub2(e10, e00), ec = sub2(e01, e00), ed = sub2(sub2(e11, e01), eb);
+    q.a1 = sub2(e00, q.a); q.b1 = sub2(eb, q.b); q.c1 = sub2(ec, q.c); q.d1 = sub2(ed, q.d);
+}
+__device__ __forceinline__ void tri2_advance(Tri2& q, f32x2 n00, f32x2 n10, f32x2 n01, f32x2 n11) {
+    q.a = add2(q.a, q.a1); q.b = add2(q.b, q.b1); q.c = add2(q.c, q.c1); q.d = add2(q.d, q.d1);
+    f32x2 eb = sub2(n10, n00);
+    q.a1 = sub2(n00, q.a); q.b1 = sub2(eb, q.b); q.c1 = sub2(sub2(n01, n00), q.c);
+    q.d1 = sub2(sub2(sub2(n11, n01), eb), q.d);
+}
+#define TT_XY(v) pk2((v).x, (v).y)
+#define TT_ZW(v) pk2((v).z, (v).w)
+
+template <bool SPC1>
+__global__ void __launch_bounds__(128, TT_EVENT_MIN_BLOCKS)
+trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
+                         const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
+                         unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A) {
+    typedef float T;
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned steps = 0;
+    if (tid < A.np) {
+        const long ray = perm ? (long)perm[tid] : tid;
+        const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
+        const size_t plane = (size_t)nu * nv;
+        // ---- prologue (identical to the scalar kernel) ----------------------------------------------
+        double X[3], D[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[k] = (s0[(size_t)A.fa[k] * A.np + ray] - A.o[k]) / A.h[k];
+            D[k] = s0[(size_t)(3 + A.fa[k]) * A.np + ray] * (1.0 / kC);
+        }
+        bool fast = X[0] >= 0.0 && X[0] <= (double)(nu - 1) && X[1] >= 0.0 && X[1] <= (double)(nv - 1) &&
+                    X[2] >= 0.0 && X[2] <= (double)(nw - 1) && D[2] > TT_MARCH_MIN_DW;
+        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * A.s_max;
+        int cu = 0, cv = 0, k = 0;
+        T tu0 = 0.f, tv0 = 0.f, fw = 0.f;
+        if (fast) {
+            double fl;
+            fl = fmin(floor(X[0]), (double)(nu - 2)); cu = (int)fl; tu0 = (T)(X[0] - fl);
+            fl = fmin(floor(X[1]), (double)(nv - 2)); cv = (int)fl; tv0 = (T)(X[1] - fl);
+            fl = floor(X[2]); k = (int)fl; fw = (T)(X[2] - fl);
+        }
+        f32x2 tuv = pk2(tu0, tv0), duv = pk2((T)D[0], (T)D[1]);
+        T dw = (T)D[2], s = 0.f;
+        const T hw = (T)A.h[2];
+        const f32x2 RUV = pk2((T)(A.h[2] / A.h[0]), (T)(A.h[2] / A.h[1]));
+        const bool track_s = sf != nullptr;
+        const int spc = A.spc;
+        const T hsub = SPC1 ? 1.f : 1.f / (T)spc;
+        int j = SPC1 ? 0 : (int)(fw * (T)spc);
+
+        if (fast && k < nw - 1) {
+            const float4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
+            Tri2 qxy, qzw;
+            float4 n00, n10, n01, n11;
+            {
+                float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
+                const float4* p1 = p + plane;
+                float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
+                tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
+                tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+            }
+            bool have_next = false;
+            while (true) {
+                if (!have_next && k + 2 <= nw - 1) {
+                    const float4* p2 = p + 2 * plane;
+                    n00 = __ldg(p2); n10 = __ldg(p2 + 1); n01 = __ldg(p2 + nu); n11 = __ldg(p2 + nu + 1);
+                    have_next = true;
+                }
+                // ---- stage 1 and the length of this step -------------------------------------------
+                T q = trcp<T>(dw), hq = hw * q;
+                bool ok = dw > T(TT_MARCH_MIN_DW);
+                f32x2 TU = bc2(lo2(tuv)), TV = bc2(hi2(tuv)), FW = bc2(fw);
+                const f32x2 aUV = mul2(mul2(RUV, duv), bc2(q));
+                const f32x2 aduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
+                const T adw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, as = hq;
+                const T fw_t = SPC1 ? 1.f : ((j + 1 == spc) ? 1.f : (T)(j + 1) * hsub);
+                T h = fw_t - fw;
+                int cross = 0;
+                {
+                    const f32x2 puv = fma2(bc2(h), aUV, tuv);
+                    const T pu = lo2(puv), pv = hi2(puv);
+                    if (pu > 1.f || pu < 0.f || pv > 1.f || pv < 0.f) {
+                        const T aU = lo2(aUV), aV = hi2(aUV), tu = lo2(tuv), tv = hi2(tuv);
+                        T lu = 2.f, lv = 2.f;
+                        if (aU > 0.f) lu = (1.f - tu) / (h * aU); else if (aU < 0.f) lu = -tu / (h * aU);
+                        if (aV > 0.f) lv = (1.f - tv) / (h * aV); else if (aV < 0.f) lv = -tv / (h * aV);
+                        T lam = fminf(lu, lv);
+                        if (lam < 1.f) {
+                            cross = lu <= lv ? (aU > 0.f ? 1 : -1) : (aV > 0.f ? 2 : -2);
+                            h *= lam > 0.f ? lam : 0.f;
+                        }
+                    }
+                }
+                const T half = 0.5f * h;
+                const f32x2 HALF = bc2(half), H = bc2(h);
+                // ---- stages 2-4 ---------------------------------------------------------------------
+                f32x2 suv = fma2(HALF, aUV, tuv), duv2 = fma2(HALF, aduv, duv);
+                T sw = fw + half, dw2 = fmaf(half, adw, dw);
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
+                TU = bc2(lo2(suv)); TV = bc2(hi2(suv)); FW = bc2(sw);
+                const f32x2 bUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 bduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
+                const T bdw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, bs = hq;
+                suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
+                TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
+                const f32x2 cUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 cduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
+                const T cdw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, cs = hq;
+                suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw); sw = fw + h;
+                q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
+                TU = bc2(lo2(suv)); TV = bc2(hi2(suv)); FW = bc2(sw);
+                const f32x2 eUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 eduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
+                const T edw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, es = hq;
+                const T h6 = h * T(1.0 / 6.0);
+                const f32x2 H6 = bc2(h6), TWO = bc2(2.f);
+                tuv = fma2(H6, add2(add2(aUV, mul2(TWO, add2(bUV, cUV))), eUV), tuv);
+                duv = fma2(H6, add2(add2(aduv, mul2(TWO, add2(bduv, cduv))), eduv), duv);
+                dw = fmaf(h6, adw + 2.f * (bdw + cdw) + edw, dw);
+                if (track_s) s = fmaf(h6, as + 2.f * (bs + cs) + es, s);
+                if (!(ok && dw > T(TT_MARCH_MIN_DW))) { fast = false; break; }
+                if (cross == 0) {
+                    ++steps;
+                    fw = fw_t;
+                    if (SPC1 || ++j == spc) {
+                        j = 0; fw = 0.f;
+                        if (++k >= nw - 1) break;
+                        p += plane;
+                        tri2_advance(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
+                        tri2_advance(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
+                        have_next = false;
+                    }
+                } else {
+                    fw += h;
+                    T tu = lo2(tuv), tv = hi2(tuv);
+                    if (cross == 1) { ++cu; tu -= 1.f; } else if (cross == -1) { --cu; tu += 1.f; }
+                    else if (cross == 2) { ++cv; tv -= 1.f; } else { --cv; tv += 1.f; }
+                    tuv = pk2(tu, tv);
+                    if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
+                    p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
+                    float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
+                    const float4* p1 = p + plane;
+                    float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
+                    tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
+                    tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+                    have_next = false;
+                }
+            }
+        }
+        if (!fast) {
+            status[ray] = TT_RAY_DEFERRED;
+            steps = 0;
+        } else {
+            const double Pu = A.o[0] + ((double)cu + (double)lo2(tuv)) * A.h[0];
+            const double Pv = A.o[1] + ((double)cv + (double)hi2(tuv)) * A.h[1];
+            const double Pw = A.o[2] + (double)(nw - 1) * A.h[2];
+            const double Vu = (double)lo2(duv) * kC, Vv = (double)hi2(duv) * kC, Vw = (double)dw * kC;
+            const double tb = (Pw - A.extent) / Vw;
+            rf[0 * A.np + ray] = Pu - Vu * tb;
+            rf[1 * A.np + ray] = atan(Vu / Vw);
+            rf[2 * A.np + ray] = Pv - Vv * tb;
+            rf[3 * A.np + ray] = atan(Vv / Vw);
+            if (sf) {
+                const double t_rest = (A.s_max - (double)s) / kC;
+                const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    sf[(size_t)A.fa[m] * A.np + ray] = Pf[m] + Vf[m] * t_rest;
+                    sf[(size_t)(3 + A.fa[m]) * A.np + ray] = Vf[m];
+                }
+            }
+            status[ray] = (uint8_t)TT_RAY_EXIT_FACE;
+        }
+    }
+    if (ray_steps) {
+        unsigned v = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
+    }
+}
+#undef TT_XY
+#undef TT_ZW
+
 // ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at arbitrary points,
 // zero outside, faces inclusive (scipy _rgi.py:635-642).
 template <typename T>
@@ -1000,12 +1215,24 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     cudaStream_t s = (cudaStream_t)stream;
     // variant: 0 = auto (event marching when a status buffer is given, else the cell-cache kernel),
     //          1 = 8-corner gather per stage, 2 = cell cache, 3 = event marching (needs status_dev)
+    //          4 = event marching without the packed FP32x2 arithmetic (cross-check of 3 in FP32)
     int variant = p->variant;
-    TT_REQUIRE(variant >= 0 && variant <= 3, "tt_trace: unknown kernel variant %d", variant);
-    TT_REQUIRE(variant != 3 || status_dev, "tt_trace: variant 3 (event marching) needs status_dev");
+    TT_REQUIRE(variant >= 0 && variant <= 4, "tt_trace: unknown kernel variant %d", variant);
+    TT_REQUIRE(variant < 3 || status_dev, "tt_trace: event marching (variant 3/4) needs status_dev");
     if (variant == 0) variant = status_dev ? 3 : 2;
     int only_flagged = 0;
-    if (variant == 3) {
+    if (variant == 3 && p->dtype == TT_F32) {
+        if (p->steps_per_cell == 1)
+            trace_event_kernel_f32x2<true><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                                              sf_dev, ray_steps_dev, status_dev, A);
+        else
+            trace_event_kernel_f32x2<false><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                                               sf_dev, ray_steps_dev, status_dev, A);
+        int rc2 = launch_check("trace_event_kernel_f32x2");
+        if (rc2) return rc2;
+        only_flagged = 1;
+        variant = 2;
+    } else if (variant >= 3) {
         const bool spc1 = p->steps_per_cell == 1;
 #define TT_LAUNCH_EV(TYPE, V4T, S1)                                                                                \
     trace_event_kernel<TYPE, S1><<<(unsigned)blocks, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev, \
