@@ -735,11 +735,21 @@ template <typename T>
 struct Tri {           // trilinear polynomial of one component in one cell
     T a, b, c, d, a1, b1, c1, d1;
 };
+// evaluation is "w first": the bilinear coefficients at w-fraction fw (4 FMA), then the bilinear form
+// (3 FMA).  RK4 stages 2 and 3 share their w-fraction, so their coefficients are formed once.
 template <typename T>
-__device__ __forceinline__ T tri_eval(const Tri<T>& q, T tu, T tv, T fw) {
-    T lo = tfma(tv, tfma(tu, q.d, q.c), tfma(tu, q.b, q.a));
-    T hi = tfma(tv, tfma(tu, q.d1, q.c1), tfma(tu, q.b1, q.a1));
-    return tfma(fw, hi, lo);
+struct Bil {
+    T a, b, c, d;
+};
+template <typename T>
+__device__ __forceinline__ Bil<T> tri_at(const Tri<T>& q, T fw) {
+    Bil<T> r;
+    r.a = tfma(fw, q.a1, q.a); r.b = tfma(fw, q.b1, q.b); r.c = tfma(fw, q.c1, q.c); r.d = tfma(fw, q.d1, q.d);
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ T bil_eval(const Bil<T>& q, T tu, T tv) {
+    return tfma(tv, tfma(tu, q.d, q.c), tfma(tu, q.b, q.a));
 }
 // coefficients of plane 0 from its 4 corners; primed = plane 1 minus plane 0
 template <typename T>
@@ -817,8 +827,8 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
                 T q = trcp<T>(dw), hq = hw * q;
                 bool ok = dw > T(TT_MARCH_MIN_DW);
                 const T aU = ru * du * q, aV = rv * dv * q;
-                const T adu = tri_eval<T>(qx, tu, tv, fw) * hq, adv = tri_eval<T>(qy, tu, tv, fw) * hq,
-                        adw = tri_eval<T>(qz, tu, tv, fw) * hq, as = hq;
+                const T adu = bil_eval<T>(tri_at<T>(qx, fw), tu, tv) * hq, adv = bil_eval<T>(tri_at<T>(qy, fw), tu, tv) * hq,
+                        adw = bil_eval<T>(tri_at<T>(qz, fw), tu, tv) * hq, as = hq;
                 const T fw_t = SPC1 ? T(1) : ((j + 1 == spc) ? T(1) : (T)(j + 1) * hsub);
                 T h = fw_t - fw;
                 int cross = 0;                         // +-1: u face, +-2: v face
@@ -841,20 +851,21 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
                 T du2 = tfma(half, adu, du), dv2 = tfma(half, adv, dv), dw2 = tfma(half, adw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
                 const T bU = ru * du2 * q, bV = rv * dv2 * q;
-                const T bdu = tri_eval<T>(qx, su, sv, sw) * hq, bdv = tri_eval<T>(qy, su, sv, sw) * hq,
-                        bdw = tri_eval<T>(qz, su, sv, sw) * hq, bs = hq;
+                const Bil<T> mx = tri_at<T>(qx, sw), my = tri_at<T>(qy, sw), mz = tri_at<T>(qz, sw);   // stages 2 and 3
+                const T bdu = bil_eval<T>(mx, su, sv) * hq, bdv = bil_eval<T>(my, su, sv) * hq,
+                        bdw = bil_eval<T>(mz, su, sv) * hq, bs = hq;
                 su = tfma(half, bU, tu); sv = tfma(half, bV, tv);
                 du2 = tfma(half, bdu, du); dv2 = tfma(half, bdv, dv); dw2 = tfma(half, bdw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
                 const T cU = ru * du2 * q, cV = rv * dv2 * q;
-                const T cdu = tri_eval<T>(qx, su, sv, sw) * hq, cdv = tri_eval<T>(qy, su, sv, sw) * hq,
-                        cdw = tri_eval<T>(qz, su, sv, sw) * hq, cs = hq;
+                const T cdu = bil_eval<T>(mx, su, sv) * hq, cdv = bil_eval<T>(my, su, sv) * hq,
+                        cdw = bil_eval<T>(mz, su, sv) * hq, cs = hq;
                 su = tfma(h, cU, tu); sv = tfma(h, cV, tv); sw = fw + h;
                 du2 = tfma(h, cdu, du); dv2 = tfma(h, cdv, dv); dw2 = tfma(h, cdw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > T(0);
                 const T eU = ru * du2 * q, eV = rv * dv2 * q;
-                const T edu = tri_eval<T>(qx, su, sv, sw) * hq, edv = tri_eval<T>(qy, su, sv, sw) * hq,
-                        edw = tri_eval<T>(qz, su, sv, sw) * hq, es = hq;
+                const T edu = bil_eval<T>(tri_at<T>(qx, sw), su, sv) * hq, edv = bil_eval<T>(tri_at<T>(qy, sw), su, sv) * hq,
+                        edw = bil_eval<T>(tri_at<T>(qz, sw), su, sv) * hq, es = hq;
                 const T h6 = h * T(1.0 / 6.0);
                 tu = tfma(h6, aU + T(2) * (bU + cU) + eU, tu);
                 tv = tfma(h6, aV + T(2) * (bV + cV) + eV, tv);
@@ -950,10 +961,16 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f
 struct Tri2 {          // two trilinear polynomials (one per lane) of one cell
     f32x2 a, b, c, d, a1, b1, c1, d1;
 };
-__device__ __forceinline__ f32x2 tri2_eval(const Tri2& q, f32x2 TU, f32x2 TV, f32x2 FW) {
-    f32x2 lo = fma2(TV, fma2(TU, q.d, q.c), fma2(TU, q.b, q.a));
-    f32x2 hi = fma2(TV, fma2(TU, q.d1, q.c1), fma2(TU, q.b1, q.a1));
-    return fma2(FW, hi, lo);
+struct Bil2 {
+    f32x2 a, b, c, d;
+};
+__device__ __forceinline__ Bil2 tri2_at(const Tri2& q, f32x2 FW) {
+    Bil2 r;
+    r.a = fma2(FW, q.a1, q.a); r.b = fma2(FW, q.b1, q.b); r.c = fma2(FW, q.c1, q.c); r.d = fma2(FW, q.d1, q.d);
+    return r;
+}
+__device__ __forceinline__ f32x2 bil2_eval(const Bil2& q, f32x2 TU, f32x2 TV) {
+    return fma2(TV, fma2(TU, q.d, q.c), fma2(TU, q.b, q.a));
 }
 __device__ __forceinline__ void tri2_set(Tri2& q, f32x2 c00, f32x2 c10, f32x2 c01, f32x2 c11, f32x2 e00, f32x2 e10,
                                          f32x2 e01, f32x2 e11) {
@@ -1011,14 +1028,16 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
 
         if (fast && k < nw - 1) {
             const float4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
-            Tri2 qxy, qzw;
+            Tri2 qxy;                 // (g_u, g_v) lanes, packed
+            Tri<float> qz;            // g_w, scalar (packing it with the unused ne/nc lane would only
+                                      // add work to the FP32 pipe, which is what bounds this kernel)
             float4 n00, n10, n01, n11;
             {
                 float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
                 const float4* p1 = p + plane;
                 float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
                 tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
-                tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+                tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
             }
             bool have_next = false;
             while (true) {
@@ -1030,10 +1049,10 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 // ---- stage 1 and the length of this step -------------------------------------------
                 T q = trcp<T>(dw), hq = hw * q;
                 bool ok = dw > T(TT_MARCH_MIN_DW);
-                f32x2 TU = bc2(lo2(tuv)), TV = bc2(hi2(tuv)), FW = bc2(fw);
+                f32x2 TU = bc2(lo2(tuv)), TV = bc2(hi2(tuv));
                 const f32x2 aUV = mul2(mul2(RUV, duv), bc2(q));
-                const f32x2 aduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
-                const T adw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, as = hq;
+                const f32x2 aduv = mul2(bil2_eval(tri2_at(qxy, bc2(fw)), TU, TV), bc2(hq));
+                const T adw = bil_eval<float>(tri_at<float>(qz, fw), lo2(tuv), hi2(tuv)) * hq, as = hq;
                 const T fw_t = SPC1 ? 1.f : ((j + 1 == spc) ? 1.f : (T)(j + 1) * hsub);
                 T h = fw_t - fw;
                 int cross = 0;
@@ -1058,22 +1077,24 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 f32x2 suv = fma2(HALF, aUV, tuv), duv2 = fma2(HALF, aduv, duv);
                 T sw = fw + half, dw2 = fmaf(half, adw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
-                TU = bc2(lo2(suv)); TV = bc2(hi2(suv)); FW = bc2(sw);
+                TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
+                const Bil2 mxy = tri2_at(qxy, bc2(sw));             // stages 2 and 3 share their w-fraction
+                const Bil<float> mz = tri_at<float>(qz, sw);
                 const f32x2 bUV = mul2(mul2(RUV, duv2), bc2(q));
-                const f32x2 bduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
-                const T bdw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, bs = hq;
+                const f32x2 bduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
+                const T bdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq, bs = hq;
                 suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
                 const f32x2 cUV = mul2(mul2(RUV, duv2), bc2(q));
-                const f32x2 cduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
-                const T cdw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, cs = hq;
+                const f32x2 cduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
+                const T cdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq, cs = hq;
                 suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw); sw = fw + h;
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
-                TU = bc2(lo2(suv)); TV = bc2(hi2(suv)); FW = bc2(sw);
+                TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
                 const f32x2 eUV = mul2(mul2(RUV, duv2), bc2(q));
-                const f32x2 eduv = mul2(tri2_eval(qxy, TU, TV, FW), bc2(hq));
-                const T edw = lo2(tri2_eval(qzw, TU, TV, FW)) * hq, es = hq;
+                const f32x2 eduv = mul2(bil2_eval(tri2_at(qxy, bc2(sw)), TU, TV), bc2(hq));
+                const T edw = bil_eval<float>(tri_at<float>(qz, sw), lo2(suv), hi2(suv)) * hq, es = hq;
                 const T h6 = h * T(1.0 / 6.0);
                 const f32x2 H6 = bc2(h6), TWO = bc2(2.f);
                 tuv = fma2(H6, add2(add2(aUV, mul2(TWO, add2(bUV, cUV))), eUV), tuv);
@@ -1089,7 +1110,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                         if (++k >= nw - 1) break;
                         p += plane;
                         tri2_advance(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
-                        tri2_advance(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
+                        tri_advance<float>(qz, n00.z, n10.z, n01.z, n11.z);
                         have_next = false;
                     }
                 } else {
@@ -1104,7 +1125,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                     const float4* p1 = p + plane;
                     float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
                     tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
-                    tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+                    tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
                     have_next = false;
                 }
             }

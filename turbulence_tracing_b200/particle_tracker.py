@@ -273,7 +273,11 @@ class ElectronCube:
         par = self._par
         fa = {2: (0, 1, 2), 1: (0, 2, 1), 0: (1, 2, 0)}[par]
         n = self.shape
-        grid = torch.empty((n[fa[2]], n[fa[1]], n[fa[0]], 4), dtype=gdt, device="cuda")
+        gshape = (n[fa[2]], n[fa[1]], n[fa[0]], 4)
+        grid = self._grid                     # rebuilt in place when the cube is only refreshed
+        if grid is None or tuple(grid.shape) != gshape or grid.dtype != gdt:
+            self._grid = grid = None          # release the old grid before allocating (2-17 GB)
+            grid = torch.empty(gshape, dtype=gdt, device="cuda")
         _lib.check(lib.tt_calc_dndr(_lib.ptr(ne_dev), _lib.dtype_code(ne_dev.dtype), _lib.i3(n), _lib.d3(spacing),
                                     par, float(self.nc), float(ne_max), _lib.ptr(grid),
                                     _lib.dtype_code(gdt), _lib.stream_ptr()), "tt_calc_dndr")
