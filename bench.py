@@ -160,25 +160,34 @@ def cpu_reference_setup(ne_host, M):
     _CPU["field"] = orc.make_field(ne_host, x, x, x, LWL)
 
 
-def cpu_reference_step(rays_per_worker, cores):
-    """Returns dict(rays, ray_rhs_evals, seconds) for one bounded sample over `cores` processes."""
+def cpu_reference_step(rays_per_worker, cores, min_seconds=10.0, max_rounds=6):
+    """One bounded sample over `cores` processes: rounds of rays_per_worker rays per process (new seeds
+    each round) until at least min_seconds of wall time (the cost of scipy's global adaptive step depends
+    strongly on the hardest ray of a bundle, so a fixed ray count gives anything from 1 s to minutes).
+    Returns dict(rays, ray_rhs_evals, seconds, rounds)."""
     import multiprocessing as mp
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[v] = "1"                      # pinned: oversubscription costs 3x (SURVEY section 6)
     ctx = mp.get_context("fork")                 # cube built once before the fork (copy-on-write)
-    t0 = time.perf_counter()
+    tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0, "rounds": 0}
     with ctx.Pool(cores) as pool:
-        out = pool.map(_cpu_worker, [(i, rays_per_worker) for i in range(cores)])
-    dt = time.perf_counter() - t0
-    return {"rays": sum(o[0] for o in out), "ray_rhs_evals": sum(o[1] for o in out), "seconds": dt}
+        while tot["rounds"] < max_rounds and tot["seconds"] < min_seconds:
+            t0 = time.perf_counter()
+            out = pool.map(_cpu_worker, [(tot["rounds"] * cores + i, rays_per_worker) for i in range(cores)])
+            tot["seconds"] += time.perf_counter() - t0
+            tot["rays"] += sum(o[0] for o in out)
+            tot["ray_rhs_evals"] += sum(o[1] for o in out)
+            tot["rounds"] += 1
+    return tot
 
 
 def cpu_line_fields(res, cores, rays_per_worker, M, kind="port"):
     steps = res["ray_rhs_evals"] / 4.0           # 4 RHS evaluations = 1 RK4-equivalent ray-step
     return {"value": steps / res["seconds"], "unit": "ray-steps/s", "cores": cores, "kind": kind,
             "rays_per_s": res["rays"] / res["seconds"],
-            "sample": f"{cores} processes x {rays_per_worker} rays on the same {M}^3 cube; scipy RK45 default "
-                      f"rtol=1e-3 (reference ElectronCube.solve), ray-steps = nfev*rays/4; {res['seconds']:.1f} s"}
+            "sample": f"{cores} processes x {res.get('rounds', 1)} bundles of {rays_per_worker} rays on the same {M}^3 "
+                      f"cube; scipy RK45 default rtol=1e-3 (reference ElectronCube.solve), ray-steps = nfev*rays/4; "
+                      f"{res['seconds']:.1f} s"}
 
 
 def run_reference_arm(args, wl):
@@ -197,10 +206,10 @@ def run_reference_arm(args, wl):
     cpu_reference_setup(ne, M)
     del ne
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(max(rays_per_worker // 4, 50), cores)
-    tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0}
+        cpu_reference_step(max(rays_per_worker // 4, 50), cores, min_seconds=0.0, max_rounds=1)
+    tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0, "rounds": 0}
     for _ in range(args.steps):
-        r = cpu_reference_step(rays_per_worker, cores)
+        r = cpu_reference_step(rays_per_worker, cores, min_seconds=10.0 if args.steps == 1 else 5.0)
         for k in tot:
             tot[k] += r[k]
     cb = cpu_line_fields(tot, cores, rays_per_worker, M)
@@ -209,7 +218,7 @@ def run_reference_arm(args, wl):
             "ms_per_step": 1e3 * tot["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "rays_per_s": cb["rays_per_s"],
-            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": cores * rays_per_worker},
+            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": tot["rays"] // max(args.steps, 1)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -417,7 +426,7 @@ def main():
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--steps-per-cell", type=int, default=1)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--cpu-rays", type=int, default=3000, help="rays per host process in the CPU baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=1000, help="rays per host process in the CPU baseline sample")
     ap.add_argument("--cube-file", default="", help="(reference arm) .npy ne cube to trace instead of a host GRF")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -174,6 +174,23 @@ def plot_afr(Rs):
     return fig, ax
 
 
+_EDGE_CACHE = {}
+
+
+def _edges_on_device(lo, hi, n):
+    """numpy.histogramdd builds its bin edges as linspace(range_min, range_max, bins + 1); they are
+    computed on the host by numpy itself and cached on the device (no per-call upload / host sync)."""
+    torch = _lib.torch_cuda()
+    key = (float(lo), float(hi), int(n), torch.cuda.current_device())
+    hit = _EDGE_CACHE.get(key)
+    if hit is None:
+        e = np.linspace(lo, hi, n + 1)
+        if len(_EDGE_CACHE) > 64:
+            _EDGE_CACHE.clear()
+        hit = _EDGE_CACHE[key] = (e, torch.from_numpy(e).cuda())
+    return hit
+
+
 # ---- detectors --------------------------------------------------------------------------------------
 class Rays:
     """Inheritable class for ray diagnostics (:156-206)."""
@@ -237,11 +254,8 @@ class Rays:
         polarisation-weighted images; the weights refer to the rays in their original order)."""
         torch = _lib.torch_cuda()
         nbx, nby = pix_x // bin_scale, pix_y // bin_scale
-        # numpy.histogramdd builds its edges with linspace(range_min, range_max, bins + 1)
-        self.xedges = np.linspace(-self.Lx / 2, self.Lx / 2, nbx + 1)
-        self.yedges = np.linspace(-self.Ly / 2, self.Ly / 2, nby + 1)
-        xe = torch.from_numpy(self.xedges).cuda()
-        ye = torch.from_numpy(self.yedges).cuda()
+        self.xedges, xe = _edges_on_device(-self.Lx / 2, self.Lx / 2, nbx)
+        self.yedges, ye = _edges_on_device(-self.Ly / 2, self.Ly / 2, nby)
         H = torch.zeros((nby, nbx), dtype=torch.int64, device="cuda")
         w = Hw = None
         if weights is not None:
