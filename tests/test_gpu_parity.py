@@ -769,3 +769,28 @@ def test_c1_end_to_end_against_reference(tt, golden, dtype, spc):
         assert np.mean(np.isnan(mine[0]) == ~ok) > 0.998
         both = ok & ~np.isnan(mine[0])
         np.testing.assert_allclose(mine[0][both], g[k + "_rf"][0][both], rtol=0, atol=1e-3 * PIXEL_M * 1e3)
+
+
+def test_pipelined_host_rays_equal_single_bundle(tt, golden):
+    """Host (numpy) rays are uploaded chunk by chunk on a copy stream while the previous chunk is traced;
+    per-ray results, status, sf and the detector image must equal the single-bundle path bit for bit."""
+    pt, rtm = tt.particle_tracker, tt.ray_transfer_matrix
+    g = golden("trace_grf33")
+    cube = pt.ElectronCube(g["x"], g["x"], g["x"], verbose=False)
+    cube.external_ne(g["ne"])
+    cube.calc_dndr()
+    cube.init_beam(5500, 4.5e-3, 5e-3, seed=3)
+    s0 = np.asarray(cube.s0).copy()
+    cube.s0 = s0
+    rf1 = np.asarray(cube.solve()); sf1 = np.asarray(cube.sf); st1 = np.asarray(cube.status); n1 = cube.ray_steps
+    sh = rtm.Shadowgraphy(cube.rf); sh.solve(); sh.histogram(); H1 = sh.H
+    cube.pipeline_chunk_rays = 1000           # 6 chunks, the last one partial
+    rf2 = np.asarray(cube.solve()); sf2 = np.asarray(cube.sf); st2 = np.asarray(cube.status)
+    assert cube.ray_steps == n1
+    np.testing.assert_array_equal(rf2, rf1)
+    np.testing.assert_array_equal(sf2, sf1)
+    np.testing.assert_array_equal(st2, st1)
+    perm = cube.rf.perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(5500))
+    sh = rtm.Shadowgraphy(cube.rf); sh.solve(); sh.histogram()
+    np.testing.assert_array_equal(sh.H, H1)

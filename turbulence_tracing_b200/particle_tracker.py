@@ -375,30 +375,19 @@ class ElectronCube:
             raise AttributeError("s0 not set: call init_beam() first")
         if not hasattr(self, "extent"):
             self.extent = (self.extent_x, self.extent_y, self.extent_z)[self._par]
-        s0 = _lib.to_device(self._s0, torch.float64)
-        if s0.dim() != 2 or s0.shape[0] not in (6, 9):
+        host = isinstance(self._s0, np.ndarray)
+        shape0 = tuple(self._s0.shape)
+        if len(shape0) != 2 or shape0[0] not in (6, 9):
             raise ValueError("s0 must have shape (6, Np) (or (9, Np) with amplitude, phase, polarisation rows)")
-        init_aux = s0[6:9] if s0.shape[0] == 9 else None
-        s0 = s0[:6].contiguous()
+        Np = shape0[1]
         use_aux = self.B_on or self.inv_brems or self.phaseshift
-        Np = s0.shape[1]
         if Np == 0:                                   # empty bundle: nothing to launch
             self.rf = DeviceArray(torch.empty((4, 0), dtype=torch.float64, device="cuda"))
             self.sf = DeviceArray(torch.empty((6, 0), dtype=torch.float64, device="cuda")) if self.keep_sf else None
-            self.status = DeviceArray(torch.empty(0, dtype=torch.uint8, device="cuda")) if return_status else None
+            self.status = DeviceArray(torch.empty(0, dtype=torch.uint8, device="cuda"))
             self._steps_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
             return self.rf
-        stream = _lib.stream_ptr()
         start = time()
-        perm = None
-        if self.sort_rays and Np > 1:
-            need = C.c_size_t(0)
-            _lib.check(lib.tt_sort_rays_workspace(Np, C.byref(need)), "tt_sort_rays_workspace")
-            ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
-            perm = torch.empty(Np, dtype=torch.int32, device="cuda")
-            _lib.check(lib.tt_sort_rays(_lib.ptr(s0), Np, self._par, _lib.d3(self._origin), _lib.d3(self._spacing),
-                                        _lib.i3(self.shape), _lib.ptr(perm), _lib.ptr(ws), need.value, stream),
-                       "tt_sort_rays")
         p = _lib.TraceParams()
         p.n_xyz[:] = self.shape
         p.origin_xyz[:] = self._origin
@@ -409,22 +398,93 @@ class ElectronCube:
         p.steps_per_cell = self.steps_per_cell
         p.dtype = _lib.dtype_code(grid.dtype)
         p.variant = int(getattr(self, "kernel_variant", 0))
-        rf = torch.empty((4, Np), dtype=torch.float64, device="cuda")
-        sf = torch.empty((6, Np), dtype=torch.float64, device="cuda") if self.keep_sf else None
-        steps = torch.zeros(1, dtype=torch.int64, device="cuda")
-        # always passed: the default kernel (event marching) flags rays for its second pass here
-        status = torch.empty(Np, dtype=torch.uint8, device="cuda")
-        events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
-        if events is not None:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
+        ap = aux4 = None
         if use_aux:
             ap = _lib.AuxParams(float(self.omega), float(self.nc), float(self.VerdetConst))
             aux4 = self._aux_grid()
-            aux_out = torch.empty((3, Np), dtype=torch.float64, device="cuda")
-            _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0), Np,
-                                        _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out), _lib.ptr(steps),
-                                        _lib.ptr(status), stream), "tt_trace_aux")
+        steps = torch.zeros(1, dtype=torch.int64, device="cuda")
+        events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
+
+        def trace_bundle(s0b, rf, sf, status, aux_out):
+            """Morton sort + trace of one device bundle s0b (6, n); returns its permutation (or None)."""
+            n = s0b.shape[1]
+            stream = _lib.stream_ptr()
+            perm = None
+            if self.sort_rays and n > 1:
+                need = C.c_size_t(0)
+                _lib.check(lib.tt_sort_rays_workspace(n, C.byref(need)), "tt_sort_rays_workspace")
+                ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+                perm = torch.empty(n, dtype=torch.int32, device="cuda")
+                _lib.check(lib.tt_sort_rays(_lib.ptr(s0b), n, self._par, _lib.d3(self._origin), _lib.d3(self._spacing),
+                                            _lib.i3(self.shape), _lib.ptr(perm), _lib.ptr(ws), need.value, stream),
+                           "tt_sort_rays")
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if use_aux:
+                _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0b), n,
+                                            _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out),
+                                            _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace_aux")
+            else:
+                _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0b), n, _lib.ptr(perm), _lib.ptr(rf),
+                                        _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
+            if events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                events.append((e0, e1))
+            return perm
+
+        def outputs(n):
+            return (torch.empty((4, n), dtype=torch.float64, device="cuda"),
+                    torch.empty((6, n), dtype=torch.float64, device="cuda") if self.keep_sf else None,
+                    # always passed: the default kernel (event marching) flags rays for its second pass here
+                    torch.empty(n, dtype=torch.uint8, device="cuda"),
+                    torch.empty((3, n), dtype=torch.float64, device="cuda") if use_aux else None)
+
+        chunk = int(getattr(self, "pipeline_chunk_rays", 12_500_000))
+        if host and Np >= 2 * chunk:
+            # ---- host rays: H2D copies of chunk i+1 overlap the trace of chunk i (two streams) ----------
+            src = torch.from_numpy(np.ascontiguousarray(self._s0[:6], dtype=np.float64))
+            rf, sf, status, aux_out = outputs(Np)
+            perm = torch.empty(Np, dtype=torch.int32, device="cuda") if self.sort_rays else None
+            main = torch.cuda.current_stream()
+            copy = getattr(self, "_copy_stream", None) or torch.cuda.Stream()
+            self._copy_stream = copy
+            bufs = [torch.empty((6, chunk), dtype=torch.float64, device="cuda") for _ in range(2)]
+            free = [None, None]                            # compute-done events per buffer
+            copy.wait_stream(main)
+            for ci, lo in enumerate(range(0, Np, chunk)):
+                n = min(chunk, Np - lo)
+                b = ci % 2
+                with torch.cuda.stream(copy):
+                    if free[b] is not None:
+                        copy.wait_event(free[b])
+                    s0b = bufs[b][:, :n] if n == chunk else bufs[b].reshape(-1)[:6 * n].view(6, n)
+                    for r in range(6):
+                        s0b[r].copy_(src[r, lo:lo + n], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(copy)
+                main.wait_event(ready)
+                rf_c, sf_c, st_c, ax_c = outputs(n)
+                pc = trace_bundle(s0b, rf_c, sf_c, st_c, ax_c)
+                rf[:, lo:lo + n] = rf_c
+                status[lo:lo + n] = st_c
+                if sf is not None:
+                    sf[:, lo:lo + n] = sf_c
+                if aux_out is not None:
+                    aux_out[:, lo:lo + n] = ax_c
+                if perm is not None:
+                    perm[lo:lo + n] = pc + lo              # global ray ids, chunk after chunk
+                free[b] = torch.cuda.Event()
+                free[b].record(main)
+            init_aux = _lib.to_device(self._s0[6:9], torch.float64) if shape0[0] == 9 else None
+        else:
+            s0 = _lib.to_device(self._s0, torch.float64)
+            init_aux = s0[6:9] if shape0[0] == 9 else None
+            s0 = s0[:6].contiguous()
+            rf, sf, status, aux_out = outputs(Np)
+            perm = trace_bundle(s0, rf, sf, status, aux_out)
+        if use_aux:
             if not self.phaseshift:
                 aux_out[1].zero_()
             if init_aux is not None:       # rows 6-8 of a 9-row s0: initial amplitude, phase, polarisation
@@ -432,15 +492,7 @@ class ElectronCube:
                 aux_out[1] += init_aux[1]
                 aux_out[2] += init_aux[2]
             self.amp, self.phase, self.pol = (DeviceArray(aux_out[i]) for i in range(3))
-            self._aux_out = aux_out
-        else:
-            self._aux_out = None
-            _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0), Np, _lib.ptr(perm), _lib.ptr(rf),
-                                    _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
-        if events is not None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            events.append((e0, e1))
+        self._aux_out = aux_out
         self._perm = perm
         if self.verbose:
             torch.cuda.current_stream().synchronize()
