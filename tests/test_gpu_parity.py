@@ -794,3 +794,46 @@ def test_pipelined_host_rays_equal_single_bundle(tt, golden):
     assert sorted(perm.tolist()) == list(range(5500))
     sh = rtm.Shadowgraphy(cube.rf); sh.solve(); sh.histogram()
     np.testing.assert_array_equal(sh.H, H1)
+
+
+def test_full_size_c2_properties(tt):
+    """BASELINE configs[1] at full size (257^3 k^-11/3 cube, 1e7 rays): size-independent properties.
+    FP32 1 step/cell against FP64 at 1 and 2 steps/cell (Richardson estimate of the truncation error),
+    every ray accounted for, dark field + light field = shadowgraphy, sorted == unsorted."""
+    import torch
+    pt, rtm, tg = tt.particle_tracker, tt.ray_transfer_matrix, tt.turboGen
+    f = tg.gaussian3D_FFT(128, lambda k: k ** (-11.0 / 3.0), seed=1234, dtype="float32", return_device=True).torch
+    assert f.shape == (257, 257, 257) and abs(float(f.mean())) < 1e-6 * float(f.std())
+    ne = 1e25 * torch.clamp(1 + 0.3 * f / f.std(), min=0)
+    x = np.linspace(-5e-3, 5e-3, 257)
+    n = 10_000_000
+    out = {}
+    for dtype, spc in (("float32", 1), ("float64", 1), ("float64", 2)):
+        cube = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=spc, verbose=False, keep_sf=False)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        cube.init_beam(n, 4e-3, 0.05e-3, seed=99)
+        rf = cube.solve()
+        assert cube.ray_steps == 256 * spc * n
+        assert int((cube.status.torch == 1).sum()) == n
+        out[(dtype, spc)] = rf
+    a, b, c = (out[k].torch for k in (("float32", 1), ("float64", 1), ("float64", 2)))
+    d32 = max(float((a[0] - b[0]).abs().max()), float((a[2] - b[2]).abs().max()))
+    dtr = max(float((b[0] - c[0]).abs().max()), float((b[2] - c[2]).abs().max()))
+    rms = float(torch.sqrt((c[1] ** 2 + c[3] ** 2).mean()))
+    dang = max(float((b[1] - c[1]).abs().max()), float((b[3] - c[3]).abs().max())) / rms
+    print(f"257^3, 1e7 rays: rms deflection {rms * 1e3:.2f} mrad; fp32 vs fp64 {d32:.2e} m = {d32 / PIXEL_M:.1e} pixel; "
+          f"1 vs 2 steps/cell {dtr:.2e} m = {dtr / PIXEL_M:.1e} pixel, angle {dang:.1e} of rms")
+    # (the FP64 <=1e-5 criterion is met with more steps per cell; 1 step/cell is the FP32 production setting)
+    assert d32 <= 1e-3 * PIXEL_M and dtr <= 1e-3 * PIXEL_M and dang <= 1e-4
+    sh = rtm.Shadowgraphy(out[("float32", 1)]); sh.solve(); sh.histogram()
+    df = rtm.Schlieren_DF(out[("float32", 1)]); df.solve(R=1); df.histogram()
+    lf = rtm.Schlieren_LF(out[("float32", 1)]); lf.solve(R=1); lf.histogram()
+    assert sh.H.sum() == n
+    np.testing.assert_array_equal(df.H + lf.H, sh.H)
+    cube.dtype = "float32"
+    cube = pt.ElectronCube(x, x, x, verbose=False, keep_sf=False, sort_rays=False)
+    cube.external_ne(ne)
+    cube.calc_dndr()
+    cube.init_beam(n, 4e-3, 0.05e-3, seed=99)
+    assert torch.equal(cube.solve().torch, a)
