@@ -404,8 +404,9 @@ def run_gpu_arm(args, wl):
                        "l2": "inputs larger than L2 (gradient grid %.2f GB, rays %.2f GB)" % (
                            M**3 * (16 if dtype == "float32" else 32) / 1e9, rays * 48 / 1e9),
                        "cube_setup_s": t_cube, "kernel_variant": args.variant},
-            "e2e": e2e, "gpu_launches": 4 * args.steps,
-            "gpu_launches_note": "per step: calc_dndr, morton_key, trace, optics_hist (+ CUB radix-sort passes)",
+            "e2e": e2e, "gpu_launches": 5 * args.steps * world,
+            "gpu_launches_note": "per step and GPU: calc_dndr_kernel, morton_key_kernel, trace_event_kernel_f32x2, trace_kernel "
+                                 "(second pass over deferred rays), optics_hist_kernel (+ 6 CUB radix-sort kernels)",
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "phases_ms": phases,
             "histogram_sum": int(H_dev.sum().item()),
         }
