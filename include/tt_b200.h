@@ -196,6 +196,18 @@ int tt_grf_nd(int ndim, int N, int dtype, const double* sqrtP_lut_dev, const dou
               const double* Wi_dev, uint64_t seed, void* out_dev, void* workspace_dev,
               size_t workspace_bytes, tt_stream_t stream);
 
+/* ---- spectrum diagnostic: calculate_spectrum_3d.spectrum_3D_scalar
+ *      (gaussian_fields/calculate_spectrum_3d.py:3-59) ----------------------------------------------
+ * Shell-averaged power |FFT(data)|^2 of a real cube data_dev[nx][ny][nz] (TT_F32 / TT_F64): one R2C
+ * cuFFT + one reduction over the half spectrum.  Shell i holds (i)*w <= |k| < (i+1)*w with
+ * w = k_max / k_bin_num and |k| built from numpy.fft.fftfreq(n, dx); shells 0 .. k_bin_num-2 are
+ * filled (the reference's loop stops there).  sum_dev / count_dev [k_bin_num]: sum of |F|^2 and number
+ * of modes per shell (the caller divides).  The input is not modified.                              */
+int tt_spectrum3d_workspace(const int n_xyz[3], int dtype, size_t* bytes);
+int tt_spectrum3d(const void* data_dev, int dtype, const int n_xyz[3], double dx, double k_max,
+                  int k_bin_num, double* sum_dev, unsigned long long* count_dev, void* workspace_dev,
+                  size_t workspace_bytes, tt_stream_t stream);
+
 /* ---- host-buffer convenience entry point (what a ctypes binding inside the reference calls) --
  * Whole path for one bundle of rays with HOST arrays: ne (C order, double) -> gradient grid ->
  * Morton sort -> trace -> rf (host, 4 x np doubles).  Allocates and frees its device scratch

@@ -161,6 +161,21 @@ def golden_traces():
     save("trace_liner", n=31, s0=cube.s0, rf=rf, sf=sf, extent=cube.extent)
 
 
+# ---------------------------------------------------------------- spectrum diagnostic
+def golden_spectrum():
+    import calculate_spectrum_3d as cs
+    rng = np.random.RandomState(5)
+    out = {}
+    np.random.seed(41)
+    f = quiet(tg.gaussian3D_FFT, 12, lambda k: k ** (-11.0 / 3.0))       # 25^3
+    out["f"] = f
+    out["k_a"], out["s_a"] = cs.spectrum_3D_scalar(f, 1.0, k_bin_num=24)
+    d = rng.randn(12, 10, 14)                                            # non-cubic, even sizes
+    out["d"] = d
+    out["k_b"], out["s_b"] = cs.spectrum_3D_scalar(d, 0.5, k_bin_num=16)
+    save("spectrum", **out)
+
+
 # ---------------------------------------------------------------- BASELINE configs[0] (C1), reduced ray count
 def golden_c1():
     """100^3 test_exponential_cos cube (parameters of example_multiprocess.py:35-38), beam 4 mm,
@@ -246,9 +261,13 @@ if __name__ == "__main__":
     if "--c1" in sys.argv:
         golden_c1()
         sys.exit(0)
+    if "--spectrum" in sys.argv:
+        golden_spectrum()
+        sys.exit(0)
     golden_calc_dndr()
     golden_init_beam()
     golden_optics()
     golden_grf()
     golden_traces()
     golden_c1()
+    golden_spectrum()

@@ -837,3 +837,22 @@ def test_full_size_c2_properties(tt):
     cube.calc_dndr()
     cube.init_beam(n, 4e-3, 0.05e-3, seed=99)
     assert torch.equal(cube.solve().torch, a)
+
+
+def test_spectrum_diagnostic_matches_reference(tt, golden):
+    """calculate_spectrum_3d.spectrum_3D_scalar on the device vs the reference's output (odd cubic
+    and even non-cubic sizes), and the k^-11/3 slope of a device-generated 257^3 cube."""
+    cs, tg = tt.calculate_spectrum_3d, tt.turboGen
+    g = golden("spectrum")
+    for data, dx, nb, kk, ss in ((g["f"], 1.0, 24, g["k_a"], g["s_a"]), (g["d"], 0.5, 16, g["k_b"], g["s_b"])):
+        k, s = cs.spectrum_3D_scalar(data, dx, k_bin_num=nb)
+        np.testing.assert_allclose(k, kk, rtol=1e-14)
+        np.testing.assert_allclose(s, ss, rtol=1e-11, equal_nan=True)
+        k32, s32 = cs.spectrum_3D_scalar(data.astype(np.float32), dx, k_bin_num=nb)
+        np.testing.assert_allclose(s32, ss, rtol=1e-4, equal_nan=True)
+    f = tg.gaussian3D_FFT(128, lambda k: k ** (-11.0 / 3.0), seed=1234, dtype="float32", return_device=True)
+    k, s = cs.spectrum_3D_scalar(f, 1.0, k_bin_num=100)
+    sel = (k > 0.03) & (k < 0.45) & np.isfinite(s) & (s > 0)
+    slope = np.polyfit(np.log(k[sel]), np.log(s[sel]), 1)[0]
+    print(f"257^3 device GRF: fitted spectral slope {slope:.3f} (target -3.667)")
+    assert slope == pytest.approx(-11.0 / 3.0, abs=0.05)

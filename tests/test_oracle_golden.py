@@ -153,3 +153,13 @@ def test_grf_matches_reference(golden):
         np.random.seed(30 + nd)
         f = orc.gaussian_fft(int(g[f"N{nd}"]), spec, ndim=nd)
         np.testing.assert_array_equal(f, g[f"f{nd}"])
+
+
+def test_spectrum_matches_reference(golden):
+    g = golden("spectrum")
+    k, s = orc.spectrum_3d_scalar(g["f"], 1.0, 24)
+    np.testing.assert_allclose(k, g["k_a"], rtol=1e-14)
+    np.testing.assert_allclose(s, g["s_a"], rtol=1e-12, equal_nan=True)
+    k, s = orc.spectrum_3d_scalar(g["d"], 0.5, 16)
+    np.testing.assert_allclose(k, g["k_b"], rtol=1e-14)
+    np.testing.assert_allclose(s, g["s_b"], rtol=1e-12, equal_nan=True)

@@ -7,6 +7,6 @@ path of jdhare/turbulence_tracing behind the reference's own Python API.
 """
 from . import _lib                                   # noqa: F401
 from ._lib import DeviceArray, TTError               # noqa: F401
-from . import particle_tracker, ray_transfer_matrix, turboGen   # noqa: F401
+from . import particle_tracker, ray_transfer_matrix, turboGen, calculate_spectrum_3d   # noqa: F401
 
-__all__ = ["particle_tracker", "ray_transfer_matrix", "turboGen", "DeviceArray", "TTError"]
+__all__ = ["particle_tracker", "ray_transfer_matrix", "turboGen", "calculate_spectrum_3d", "DeviceArray", "TTError"]

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "tt_grf3d": (_i, [_i, _i, _vp, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
     "tt_grf_nd_workspace": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "tt_grf_nd": (_i, [_i, _i, _i, _vp, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
+    "tt_spectrum3d_workspace": (_i, [C.POINTER(_I3), _i, C.POINTER(_sz)]),
+    "tt_spectrum3d": (_i, [_vp, _i, C.POINTER(_I3), _d, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "tt_solve_host": (_i, [_vp, C.POINTER(_I3), C.POINTER(_D3), C.POINTER(_D3), _i, _d, _d, _d, _i, _i, _vp, _l,
                            _vp, _vp, C.POINTER(C.c_ulonglong)]),
 }
