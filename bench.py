@@ -42,6 +42,7 @@ WORKLOADS = {
     # name: (N_half of gaussian3D_FFT -> M = 2N+1 points per axis, rays per GPU, BASELINE config)
     "c3": (256, 100_000_000, "configs[2]: 513^3 (gaussian3D_FFT N=256) k^-11/3 GRF ne cube, 1e8 rays per GPU, shadowgraphy"),
     "c2": (128, 10_000_000, "configs[1]: 257^3 (gaussian3D_FFT N=128) k^-11/3 GRF ne cube, 1e7 rays per GPU, shadowgraphy"),
+    "c5": (512, 125_000_000, "configs[4] per-GPU share: 1025^3 (gaussian3D_FFT N=512) k^-11/3 GRF ne cube (17.2 GB float4 grid), 1.25e8 rays per GPU (1e9 on 8), shadowgraphy"),
     "c1": (32, 100_000, "smoke-size: 65^3 GRF cube, 1e5 rays"),
 }
 BEAM_SIZE, DIVERGENCE, EXTENT, LWL = 4e-3, 0.05e-3, 5e-3, 1053e-9

@@ -174,3 +174,19 @@ def test_spectrum_table():
     q = np.arange(1, 3 * N * N + 1)
     np.testing.assert_allclose(lut[1:], (np.sqrt(q) / (2 * N + 1)) ** (-11.0 / 6.0), rtol=1e-14)
     assert np.all(tg._sqrt_spectrum_table(N, lambda k: 2.0)[1:] == np.sqrt(2.0))   # scalar-valued k_func
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU arm): one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "1", "--warmup", "0", "--cpu-rays", "40"], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "ray-steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]

@@ -847,12 +847,31 @@ def test_spectrum_diagnostic_matches_reference(tt, golden):
     for data, dx, nb, kk, ss in ((g["f"], 1.0, 24, g["k_a"], g["s_a"]), (g["d"], 0.5, 16, g["k_b"], g["s_b"])):
         k, s = cs.spectrum_3D_scalar(data, dx, k_bin_num=nb)
         np.testing.assert_allclose(k, kk, rtol=1e-14)
-        np.testing.assert_allclose(s, ss, rtol=1e-11, equal_nan=True)
+        tiny = 1e-12 * np.nanmax(ss)          # the DC shell of a zero-mean field is rounding noise
+        np.testing.assert_allclose(s, ss, rtol=1e-11, atol=tiny, equal_nan=True)
         k32, s32 = cs.spectrum_3D_scalar(data.astype(np.float32), dx, k_bin_num=nb)
-        np.testing.assert_allclose(s32, ss, rtol=1e-4, equal_nan=True)
+        np.testing.assert_allclose(s32, ss, rtol=1e-4, atol=1e-8 * np.nanmax(ss), equal_nan=True)
     f = tg.gaussian3D_FFT(128, lambda k: k ** (-11.0 / 3.0), seed=1234, dtype="float32", return_device=True)
     k, s = cs.spectrum_3D_scalar(f, 1.0, k_bin_num=100)
     sel = (k > 0.03) & (k < 0.45) & np.isfinite(s) & (s > 0)
     slope = np.polyfit(np.log(k[sel]), np.log(s[sel]), 1)[0]
     print(f"257^3 device GRF: fitted spectral slope {slope:.3f} (target -3.667)")
     assert slope == pytest.approx(-11.0 / 3.0, abs=0.05)
+
+
+def test_example_scripts_run(tt):
+    """the two example flows (kitchen sink with B field / Jones vectors; sharded shadowgraphy)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "kitchensink_synthetic.py"), "20000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "mean Faraday rotation" in out.stdout
+    rot = float(out.stdout.split("mean Faraday rotation")[1].split("mrad")[0])
+    est = float(out.stdout.split("V*ne*B*L =")[1].split("mrad")[0])
+    assert rot == pytest.approx(est, rel=0.05)
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "multi_gpu_shadowgraphy.py"), "200000", "16"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "200000 rays, 6400000 ray-steps" in out.stdout

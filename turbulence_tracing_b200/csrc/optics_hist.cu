@@ -5,10 +5,11 @@
 // One thread handles kRaysPerThread rays; the 4-vector (x, theta, y, phi) lives in registers
 // while the whole element program is applied (FP64, 32 B read per ray), then the ray is binned.
 // Binning is privatised per CTA: a kTile x kTile window of uint32 counters in shared memory is
-// anchored at the smallest bin touched by the CTA's rays; with Morton-ordered rays (perm) a CTA's
-// rays land in a compact patch of the detector, so almost every increment is a shared-memory
-// atomic and the window is flushed once with one global atomic per non-empty bin.  Rays outside
-// the window fall through to a global atomic.
+// anchored at the smallest bin touched by the CTA's rays; when a CTA's rays land in a compact patch
+// of the detector (spatially ordered rays, or the Morton order of the trace via perm) almost every
+// increment is a shared-memory atomic and the window is flushed once with one global atomic per
+// non-empty bin.  Rays outside the window fall through to a global atomic (unordered beams: ~4e10
+// atomics/s on B200, still faster than a permuted gather of the rays -- see ray_transfer_matrix.py).
 #include "common.cuh"
 
 namespace tt {

@@ -544,8 +544,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
     bool mine = tid < A.np;
     long ray = 0;
     if (mine) {
-        ray = perm ? (long)perm[tid] : tid;
-        // second pass behind trace_event_kernel: only the rays it handed over
+        // second pass behind trace_event_kernel: only the rays it handed over, visited in ray order
+        // (a coalesced scan of the flags; the Morton order only matters for the bulk of the rays)
+        ray = (perm && !only_flagged) ? (long)perm[tid] : tid;
         if (only_flagged && status[ray] != TT_RAY_DEFERRED) mine = false;
     }
     if (mine) {
