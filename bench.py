@@ -222,7 +222,7 @@ def run_reference_arm(args, wl):
             "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": tot["rays"] // max(args.steps, 1)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -411,13 +411,35 @@ def run_gpu_arm(args, wl):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "phases_ms": phases,
             "histogram_sum": int(H_dev.sum().item()),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything that native libraries print to fd 1 (e.g. "NCCL version ...") goes to stderr; the ONE JSON
+    line of the contract is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
