@@ -38,6 +38,10 @@ struct TraceArgs {
     double extent, s_max;
     int spc;
     long np;
+    // precomputed for the event kernels (operands straight from the constant bank: no in-loop 64-bit
+    // multiplies, no double->float conversions)
+    long long plane_elems;   // nu * nv
+    float hwf, ruf, rvf;     // (float) h_w, h_w/h_u, h_w/h_v
 };
 
 template <typename T> struct GridT;
@@ -784,7 +788,7 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
     if (tid < A.np) {
         const long ray = perm ? (long)perm[tid] : tid;
         const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
-        const size_t plane = (size_t)nu * nv;
+        const long long plane = A.plane_elems;
         // ---- prologue ---------------------------------------------------------------------------
         double X[3], D[3];
 #pragma unroll
@@ -903,10 +907,9 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
                 } else {
                     // ---- reached a u / v cell face inside the w-cell: relabel and reload ---------
                     fw += h;
-                    if (cross == 1) { ++cu; tu -= T(1); } else if (cross == -1) { --cu; tu += T(1); }
-                    else if (cross == 2) { ++cv; tv -= T(1); } else { --cv; tv += T(1); }
+                    if (cross == 1) { ++cu; tu -= T(1); p += 1; } else if (cross == -1) { --cu; tu += T(1); p -= 1; }
+                    else if (cross == 2) { ++cv; tv -= T(1); p += nu; } else { --cv; tv += T(1); p -= nu; }
                     if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }   // side exit
-                    p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
                     V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
                     const V4* p1 = p + plane;
                     V4 e00 = GridT<T>::ld(p1), e10 = GridT<T>::ld(p1 + 1), e01 = GridT<T>::ld(p1 + nu), e11 = GridT<T>::ld(p1 + nu + 1);
@@ -1009,7 +1012,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
     if (tid < A.np) {
         const long ray = perm ? (long)perm[tid] : tid;
         const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
-        const size_t plane = (size_t)nu * nv;
+        const long long plane = A.plane_elems;
         // ---- prologue (identical to the scalar kernel) ----------------------------------------------
         double X[3], D[3];
 #pragma unroll
@@ -1030,8 +1033,8 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
         }
         f32x2 tuv = pk2(tu0, tv0), duv = pk2((T)D[0], (T)D[1]);
         T dw = (T)D[2], s = 0.f;
-        const T hw = (T)A.h[2];
-        const f32x2 RUV = pk2((T)(A.h[2] / A.h[0]), (T)(A.h[2] / A.h[1]));
+        const T hw = A.hwf;
+        const f32x2 RUV = pk2(A.ruf, A.rvf);
         const bool track_s = sf != nullptr;
         const int spc = A.spc;
         const T hsub = SPC1 ? 1.f : 1.f / (T)spc;
@@ -1131,11 +1134,10 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 } else {
                     fw += h;
                     T tu = lo2(tuv), tv = hi2(tuv);
-                    if (cross == 1) { ++cu; tu -= 1.f; } else if (cross == -1) { --cu; tu += 1.f; }
-                    else if (cross == 2) { ++cv; tv -= 1.f; } else { --cv; tv += 1.f; }
+                    if (cross == 1) { ++cu; tu -= 1.f; p += 1; } else if (cross == -1) { --cu; tu += 1.f; p -= 1; }
+                    else if (cross == 2) { ++cv; tv -= 1.f; p += nu; } else { --cv; tv += 1.f; p -= nu; }
                     tuv = pk2(tu, tv);
                     if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
-                    p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
                     float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
                     const float4* p1 = p + plane;
                     float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
@@ -1225,6 +1227,8 @@ static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3
         TT_REQUIRE(A.n[k] >= 2, "every axis needs >= 2 points");
         TT_REQUIRE(A.h[k] > 0, "spacing must be > 0");
     }
+    A.plane_elems = (long long)A.n[0] * A.n[1];
+    A.hwf = (float)A.h[2]; A.ruf = (float)(A.h[2] / A.h[0]); A.rvf = (float)(A.h[2] / A.h[1]);
     return TT_OK;
 }
 
