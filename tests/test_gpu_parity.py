@@ -875,3 +875,39 @@ def test_example_scripts_run(tt):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "200000 rays, 6400000 ray-steps" in out.stdout
+
+
+def test_composed_program_and_pickling(tt, golden):
+    """A user-composed element chain runs fused and equals the element functions applied one by one;
+    detectors stay picklable (example_MPI.py:152-166 pickles them after clear_rays)."""
+    import pickle
+    rtm = tt.ray_transfer_matrix
+    g = golden("optics")
+    r0 = g["r0"]
+    prog = (rtm.OpticsProgram().distance(350).circular_aperture(25).lens(400, 200).distance(300)
+            .knife_edge(0.5, "y", 1).rect_aperture(30, 20).angular_filter([0.0, 0.4]).circular_stop(0.2).sym_lens(250).distance(120))
+    assert len(prog) == 10
+    d = rtm.Rays(r0, Lx=40, Ly=40)
+    d.solve_program(prog)
+    r = rtm.m_to_mm(r0)
+    r = rtm.distance(r, 350); r = rtm.circular_aperture(r, 25); r = rtm.lens(r, 400, 200); r = rtm.distance(r, 300)
+    r = rtm.knife_edge(r, 0.5, "y", 1); r = rtm.rect_aperture(r, 30, 20); r = rtm.angular_filter(r, [0.0, 0.4])
+    r = rtm.circular_stop(r, 0.2); r = rtm.sym_lens(r, 250); r = rtm.distance(r, 120)
+    np.testing.assert_array_equal(np.asarray(d.rf), np.asarray(r))
+    assert 0.05 < np.mean(~np.isnan(np.asarray(d.rf)[0])) < 0.95
+    # the same chain with the oracle's element functions
+    o = orc.m_to_mm(r0)
+    o = orc.distance(o, 350); o = orc.circular_aperture(o, 25); o = orc.lens(o, 400, 200); o = orc.distance(o, 300)
+    o = orc.knife_edge(o, 0.5, "y", 1); o = orc.rect_aperture(o, 30, 20); o = orc.angular_filter(o, [0.0, 0.4])
+    o = orc.circular_stop(o, 0.2); o = orc.sym_lens(o, 250); o = orc.distance(o, 120)
+    np.testing.assert_allclose(np.asarray(d.rf), o, rtol=1e-13, atol=1e-13, equal_nan=True)
+    d.histogram(bin_scale=25, clear_mem=True)
+    Href, _, _ = orc.histogram(o, Lx=40, Ly=40, bin_scale=25)
+    np.testing.assert_array_equal(d.H, Href)
+    d2 = pickle.loads(pickle.dumps(d))
+    np.testing.assert_array_equal(d2.H, d.H)
+    assert d2.rf is None and d2.Lx == 40
+    sh = rtm.Shadowgraphy(r0); sh.solve()
+    sh2 = pickle.loads(pickle.dumps(sh))                 # with rays still attached
+    sh2.histogram(); sh.histogram()
+    np.testing.assert_array_equal(sh2.H, sh.H)

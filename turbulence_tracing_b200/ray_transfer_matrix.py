@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import DeviceArray
 
-__all__ = ["m_to_mm", "lens", "sym_lens", "distance", "circular_aperture", "circular_stop", "annular_stop",
+__all__ = ["OpticsProgram", "m_to_mm", "lens", "sym_lens", "distance", "circular_aperture", "circular_stop", "annular_stop",
            "angular_filter", "rect_aperture", "knife_edge", "plot_afr", "Rays", "Shadowgraphy", "Schlieren_DF",
            "Schlieren_LF", "AFR", "Refractometer", "ShadowgraphyRays", "SchlierenRays", "BurdiscopeRays"]
 
@@ -191,6 +191,50 @@ def _edges_on_device(lo, hi, n):
     return hit
 
 
+class OpticsProgram:
+    """A user-composed chain of the reference's optical elements that runs as ONE fused kernel pass
+    (instead of one array pass per element function):
+
+        prog = OpticsProgram().distance(400).circular_aperture(25).lens(400, 200).knife_edge(0.5, 'y', 1)
+        det = Rays(rf); det.solve_program(prog.distance(400)); det.histogram()
+
+    Each method appends the element with the semantics of the function of the same name
+    (ray_transfer_matrix.py:42-154)."""
+
+    def __init__(self, ops=None):
+        self.ops = list(ops or [])
+
+    def _add(self, *ops):
+        return OpticsProgram(self.ops + list(ops))
+
+    def distance(self, d):
+        return self._add(_op_distance(d))
+
+    def lens(self, f1, f2):
+        return self._add(_op_lens(f1, f2))
+
+    def sym_lens(self, f):
+        return self._add(_op_lens(f, f))
+
+    def circular_aperture(self, R):
+        return self._add(_op(_lib.OP_CIRC_APERTURE, R))
+
+    def circular_stop(self, R):
+        return self._add(_op(_lib.OP_CIRC_STOP, R))
+
+    def angular_filter(self, Rs):
+        return self._add(*_ops_angular_filter(Rs))
+
+    def rect_aperture(self, Lx, Ly):
+        return self._add(_op(_lib.OP_RECT_APERTURE, Lx, Ly))
+
+    def knife_edge(self, offset, axis, direction):
+        return self._add(_op_knife(offset, axis, direction))
+
+    def __len__(self):
+        return len(self.ops)
+
+
 # ---- detectors --------------------------------------------------------------------------------------
 class Rays:
     """Inheritable class for ray diagnostics (:156-206)."""
@@ -211,6 +255,9 @@ class Rays:
         self._rf = None
         self.H_dev = None
 
+    def _perm_dev(self):
+        return None if self._perm is None else _lib.to_device(self._perm)
+
     def use_ray_order(self, perm):
         """Visit the rays in the order perm[0..N) (int32 device tensor, e.g. ``cube.rf.perm``)."""
         self._perm = perm
@@ -221,7 +268,7 @@ class Rays:
         if self._r0_m is None:
             return None
         if self._r0_mm is None:
-            t = self._r0_m.clone()
+            t = _lib.to_device(self._r0_m).clone()
             t[0::2] *= 1e3
             self._r0_mm = DeviceArray(t)
         return self._r0_mm
@@ -240,10 +287,14 @@ class Rays:
         self._program = list(program)
         self._rf = None
 
+    def solve_program(self, program):
+        """Custom detector: propagate r0 (mm) through a user-composed :class:`OpticsProgram`."""
+        self._set_program(program.ops if isinstance(program, OpticsProgram) else program)
+
     @property
     def rf(self):
         if self._rf is None and self._program is not None and self._r0_m is not None:
-            self._rf = DeviceArray(_run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm))
+            self._rf = DeviceArray(_run(_lib.to_device(self._r0_m), self._program, pos_scale=1e3, perm=self._perm_dev()))
         return self._rf
 
     @rf.setter
@@ -270,13 +321,15 @@ class Rays:
             w = _lib.to_device(weights, torch.float64).reshape(-1)
             Hw = torch.zeros((nby, nbx), dtype=torch.float64, device="cuda")
         if self._rf is not None:                      # rays already at the detector plane
-            if w is not None and w.numel() != self._rf.torch.shape[1]:
+            rfd = _lib.to_device(self._rf, torch.float64)
+            if w is not None and w.numel() != rfd.shape[1]:
                 raise ValueError("weights must have one entry per ray")
-            _run(self._rf.torch, [], perm=self._perm, hist=(xe, ye, H), want_rf=False, weights=w, Hw=Hw)
+            _run(rfd, [], perm=self._perm_dev(), hist=(xe, ye, H), want_rf=False, weights=w, Hw=Hw)
         elif self._program is not None and self._r0_m is not None:   # fused: optics + binning, one pass
-            if w is not None and w.numel() != self._r0_m.shape[1]:
+            r0d = _lib.to_device(self._r0_m, torch.float64)
+            if w is not None and w.numel() != r0d.shape[1]:
                 raise ValueError("weights must have one entry per ray")
-            _run(self._r0_m, self._program, pos_scale=1e3, perm=self._perm, hist=(xe, ye, H), want_rf=False,
+            _run(r0d, self._program, pos_scale=1e3, perm=self._perm_dev(), hist=(xe, ye, H), want_rf=False,
                  weights=w, Hw=Hw)
         else:
             raise AttributeError("no rays to bin: call solve() first")
@@ -298,21 +351,18 @@ class Rays:
         self._program = None
         self._perm = None
 
-    def __getstate__(self):          # detectors stay picklable (example_MPI.py:152-166)
+    def __getstate__(self):          # detectors stay picklable (example_MPI.py:152-166); device data -> numpy
         d = dict(self.__dict__)
-        for k in ("_r0_m", "_r0_mm", "_rf", "_perm", "H_dev"):
+        for k in ("_r0_m", "_r0_mm", "_rf", "_perm", "H_dev", "Hw_dev"):
             v = d.get(k)
             if v is not None:
-                d[k] = np.asarray(v.cpu() if hasattr(v, "cpu") else v)
+                d[k] = np.asarray(v.detach().cpu() if hasattr(v, "detach") else v)
         return d
 
     def __setstate__(self, d):
+        # host arrays are kept as they are (a pickle can be opened without a GPU, e.g. for plotting H);
+        # they are uploaded again on first use
         self.__dict__.update(d)
-        for k in ("_r0_mm", "_rf"):
-            if isinstance(d.get(k), np.ndarray):
-                self.__dict__[k] = None
-        for k in ("_r0_m", "_perm", "H_dev"):
-            self.__dict__[k] = None if not isinstance(d.get(k), np.ndarray) else d[k]
 
 
 class Shadowgraphy(Rays):
