@@ -43,6 +43,8 @@ WORKLOADS = {
     "c3": (256, 100_000_000, "configs[2]: 513^3 (gaussian3D_FFT N=256) k^-11/3 GRF ne cube, 1e8 rays per GPU, shadowgraphy"),
     "c2": (128, 10_000_000, "configs[1]: 257^3 (gaussian3D_FFT N=128) k^-11/3 GRF ne cube, 1e7 rays per GPU, shadowgraphy"),
     "c5": (512, 125_000_000, "configs[4] per-GPU share: 1025^3 (gaussian3D_FFT N=512) k^-11/3 GRF ne cube (17.2 GB float4 grid), 1.25e8 rays per GPU (1e9 on 8), shadowgraphy"),
+    "c4": (128, 10_000_000, "configs[3]: 257^3 GRF ne cube + B cube (10 T along the beam + GRF perturbation) + Te cube, 1e7 rays per GPU, "
+                            "phase + Faraday rotation + inverse-bremsstrahlung attenuation, shadowgraphy"),
     "c1": (32, 100_000, "smoke-size: 65^3 GRF cube, 1e5 rays"),
 }
 BEAM_SIZE, DIVERGENCE, EXTENT, LWL = 4e-3, 0.05e-3, 5e-3, 1053e-9
@@ -254,9 +256,27 @@ def run_gpu_arm(args, wl):
     torch.cuda.synchronize()
     t_cube = time.perf_counter() - t0
 
+    aux = wl == "c4"
+    if aux:                                    # magnetised / absorbing plasma (parity unpinned)
+        Bvec = torch.zeros((M, M, M, 3), dtype=torch.float32, device=dev)
+        Te = torch.empty((M, M, M), dtype=torch.float32, device=dev)
+        if rank == 0:
+            g1 = tg.gaussian3D_FFT(n_half, SPECTRUM, seed=77, dtype="float32", return_device=True).torch
+            Bvec[..., 2] = 10.0
+            Bvec[..., 0] = 2.0 * g1 / g1.std()
+            Te.copy_(100.0 * torch.clamp(1 + 0.2 * g1 / g1.std(), min=0.1))
+            del g1
+        ttd.broadcast_cube(Bvec, src=0)
+        ttd.broadcast_cube(Te, src=0)
+
     def make_cube():
-        c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=args.steps_per_cell, keep_sf=False, verbose=False)
+        c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=args.steps_per_cell, keep_sf=False, verbose=False,
+                            B_on=aux, inv_brems=aux, phaseshift=aux)
         c.kernel_variant = args.variant
+        if aux:
+            c.external_B(Bvec)
+            c.external_Te(Te)
+            c.external_Z(1.0)
         return c
 
     cube = make_cube()
@@ -365,7 +385,8 @@ def run_gpu_arm(args, wl):
 
     # ---- roofline of the dominant kernel (trace) ---------------------------------------------------
     peak, peak_src = measured_hbm_peak()
-    bytes_per_step = ALGO_BYTES_PER_RAY_STEP * (2 if dtype == "float64" else 1)
+    # FP64: 32-byte corners; config 4: a second float4 grid (B, kappa) is gathered at every corner
+    bytes_per_step = ALGO_BYTES_PER_RAY_STEP * (2 if dtype == "float64" else 1) * (2 if aux else 1)
     achieved = steps_per_launch * bytes_per_step / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "trace_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic(wl, dtype, args.variant) if not args.rays else None,

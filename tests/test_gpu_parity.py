@@ -659,6 +659,35 @@ def test_aux_random_fields_match_scipy_integration(tt, golden):
     np.testing.assert_allclose(amp, amp_o, rtol=1e-6)
     rf32, amp32, ph32, pol32 = res["float32"]
     print(f"aux fp32: phase err {np.abs(ph32 - ph_o).max():.2e} rad, rotation err {np.abs(pol32 - pol_o).max():.2e}")
+    # FP32 runs the event-marching kernel with the passive quantities on board; the gather kernel
+    # (variant 1) is the cross-check, also on a wide beam with side exits (second pass) and 1 step/cell
+    for spc, beam in ((4, None), (1, 5.2e-3)):
+        out = {}
+        for variant in (0, 1):
+            cube = _aux_cube(tt, x, ne, B, Te, "float32", spc)
+            cube.kernel_variant = variant
+            if beam is None:
+                cube.s0 = s0
+                cube.extent = float(g["extent"])
+            else:
+                cube.init_beam(100_000, beam, 2e-2, seed=6)
+            rfv = np.asarray(cube.solve())
+            out[variant] = (rfv, np.asarray(cube.amp), np.asarray(cube.phase), np.asarray(cube.pol), np.asarray(cube.status))
+        a, b = out[0], out[1]
+        np.testing.assert_array_equal(a[4] & 11, b[4] & 11)
+        fastpath = (a[4] & 27) == 1                  # rays that stayed on the fast path in both kernels
+        assert fastpath.mean() > 0.5
+        # (two different step patterns on a coarse 33^3 cube: they differ by their truncation errors)
+        dpos = np.abs(a[0][0::2][:, fastpath] - b[0][0::2][:, fastpath]).max()
+        dang = np.abs(a[0][1::2][:, fastpath] - b[0][1::2][:, fastpath]).max()
+        dph = np.abs(a[2][fastpath] - b[2][fastpath]).max()
+        dpol = np.abs(a[3][fastpath] - b[3][fastpath]).max() / np.abs(b[3]).max()
+        damp = np.abs(a[1][fastpath] / b[1][fastpath] - 1).max()
+        print(f"aux event vs gather kernel, spc={spc}: pos {dpos:.1e} m, angle {dang:.1e} rad, phase {dph:.1e} rad, "
+              f"rotation {dpol:.1e} (rel), amplitude {damp:.1e} (rel)")
+        assert dpos <= 5e-7 / spc**2 and dang <= 5e-5 / spc**2
+        assert dph <= 2e-2 / spc and dpol <= 2e-3 / spc and damp <= 2e-4   # of ~400 rad / O(1) / O(1)
+        np.testing.assert_array_equal(a[2][~fastpath], b[2][~fastpath])     # deferred rays: same kernel, same bits
     np.testing.assert_allclose(ph32, ph_o, rtol=0, atol=5e-3)
     np.testing.assert_allclose(pol32, pol_o, rtol=0, atol=1e-4 * np.abs(pol_o).max())
     np.testing.assert_allclose(amp32, amp_o, rtol=1e-5)

@@ -1003,11 +1003,28 @@ __device__ __forceinline__ void tri2_advance(Tri2& q, f32x2 n00, f32x2 n10, f32x
 #define TT_XY(v) pk2((v).x, (v).y)
 #define TT_ZW(v) pk2((v).z, (v).w)
 
-template <bool SPC1>
-__global__ void __launch_bounds__(128, TT_EVENT_MIN_BLOCKS)
+// AUX = true additionally carries the passive quantities of tt_trace_aux (phase, Faraday rotation,
+// absorption): the ne/nc lane rides with g_w as a packed pair, a second grid (B_u, B_v | B_w, kappa) gets
+// two more packed polynomials, and the RK4 stages double as Simpson nodes of the three line integrals.
+__device__ __forceinline__ void aux_integrands(float nn, f32x2 bxy, f32x2 bzk, f32x2 duv, float dw, float hq, bool has_b,
+                                               float& fp, float& ff, float& fa) {
+    const float r = sqrtf(fmaxf(1.f - nn, 0.f));
+    fp = -nn / (1.f + r) * hq;                      // (sqrt(1 - ne/nc) - 1) ds, without cancellation
+    ff = 0.f; fa = 0.f;
+    if (has_b) {
+        const float bd = fmaf(lo2(bxy), lo2(duv), fmaf(hi2(bxy), hi2(duv), lo2(bzk) * dw));
+        ff = nn * bd * hq;                          // (ne/nc) (B . d) ds
+        fa = hi2(bzk) * hq;                         // kappa ds
+    }
+}
+
+template <bool SPC1, bool AUX>
+__global__ void __launch_bounds__(128, AUX ? 3 : TT_EVENT_MIN_BLOCKS)
 trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
                          const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
-                         unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A) {
+                         unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A,
+                         const float4* __restrict__ aux4 = nullptr, double* __restrict__ aux_out = nullptr,
+                         AuxArgs AX = AuxArgs()) {
     typedef float T;
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned steps = 0;
@@ -1041,20 +1058,34 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
         const int spc = A.spc;
         const T hsub = SPC1 ? 1.f : 1.f / (T)spc;
         int j = SPC1 ? 0 : (int)(fw * (T)spc);
+        double acc_p = 0.0, acc_f = 0.0, acc_a = 0.0;     // AUX: line integrals of (n-1), (ne/nc)(B.d), kappa
 
         if (fast && k < nw - 1) {
             const float4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
             Tri2 qxy;                 // (g_u, g_v) lanes, packed
             Tri<float> qz;            // g_w, scalar (packing it with the unused ne/nc lane would only
                                       // add work to the FP32 pipe, which is what bounds this kernel)
+            Tri2 qzw, bxy, bzk;       // AUX: (g_w, ne/nc), (B_u, B_v), (B_w, kappa)
+            const bool has_b = AUX && aux4 != nullptr;
+            const float4* pa = has_b ? aux4 + (p - grid) : nullptr;
             float4 n00, n10, n01, n11;
-            {
+            // (re)build the polynomials of the current cell from planes k and k+1
+            auto load_cell = [&]() {
                 float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
                 const float4* p1 = p + plane;
                 float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
                 tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
-                tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
-            }
+                if (AUX) tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+                else tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
+                if (has_b) {
+                    c00 = __ldg(pa); c10 = __ldg(pa + 1); c01 = __ldg(pa + nu); c11 = __ldg(pa + nu + 1);
+                    const float4* q1 = pa + plane;
+                    e00 = __ldg(q1); e10 = __ldg(q1 + 1); e01 = __ldg(q1 + nu); e11 = __ldg(q1 + nu + 1);
+                    tri2_set(bxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
+                    tri2_set(bzk, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
+                }
+            };
+            load_cell();
             bool have_next = false;
             while (true) {
                 if (!have_next && k + 2 <= nw - 1) {
@@ -1068,7 +1099,19 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 f32x2 TU = bc2(lo2(tuv)), TV = bc2(hi2(tuv));
                 const f32x2 aUV = mul2(mul2(RUV, duv), bc2(q));
                 const f32x2 aduv = mul2(bil2_eval(tri2_at(qxy, bc2(fw)), TU, TV), bc2(hq));
-                const T adw = bil_eval<float>(tri_at<float>(qz, fw), lo2(tuv), hi2(tuv)) * hq, as = hq;
+                T adw, as = hq;
+                float fp1 = 0.f, ff1 = 0.f, fa1 = 0.f, fp2 = 0.f, ff2 = 0.f, fa2 = 0.f, fp3 = 0.f, ff3 = 0.f, fa3 = 0.f,
+                      fp4 = 0.f, ff4 = 0.f, fa4 = 0.f;
+                if (AUX) {
+                    const f32x2 FW = bc2(fw);
+                    const f32x2 gzw = bil2_eval(tri2_at(qzw, FW), TU, TV);
+                    adw = lo2(gzw) * hq;
+                    f32x2 b1 = 0, b2 = 0;
+                    if (has_b) { b1 = bil2_eval(tri2_at(bxy, FW), TU, TV); b2 = bil2_eval(tri2_at(bzk, FW), TU, TV); }
+                    aux_integrands(hi2(gzw), b1, b2, duv, dw, hq, has_b, fp1, ff1, fa1);
+                } else {
+                    adw = bil_eval<float>(tri_at<float>(qz, fw), lo2(tuv), hi2(tuv)) * hq;
+                }
                 const T fw_t = SPC1 ? 1.f : ((j + 1 == spc) ? 1.f : (T)(j + 1) * hsub);
                 T h = fw_t - fw;
                 int cross = 0;
@@ -1096,28 +1139,70 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
                 const Bil2 mxy = tri2_at(qxy, bc2(sw));             // stages 2 and 3 share their w-fraction
-                const Bil<float> mz = tri_at<float>(qz, sw);
+                Bil<float> mz;
+                Bil2 mzw, mb1, mb2;
+                if (AUX) {
+                    mzw = tri2_at(qzw, bc2(sw));
+                    if (has_b) { mb1 = tri2_at(bxy, bc2(sw)); mb2 = tri2_at(bzk, bc2(sw)); }
+                } else {
+                    mz = tri_at<float>(qz, sw);
+                }
                 const f32x2 bUV = mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 bduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
-                const T bdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq, bs = hq;
+                T bdw, bs = hq;
+                if (AUX) {
+                    const f32x2 gzw = bil2_eval(mzw, TU, TV);
+                    bdw = lo2(gzw) * hq;
+                    f32x2 b1 = 0, b2 = 0;
+                    if (has_b) { b1 = bil2_eval(mb1, TU, TV); b2 = bil2_eval(mb2, TU, TV); }
+                    aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp2, ff2, fa2);
+                } else {
+                    bdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq;
+                }
                 suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
                 const f32x2 cUV = mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 cduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
-                const T cdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq, cs = hq;
+                T cdw, cs = hq;
+                if (AUX) {
+                    const f32x2 gzw = bil2_eval(mzw, TU, TV);
+                    cdw = lo2(gzw) * hq;
+                    f32x2 b1 = 0, b2 = 0;
+                    if (has_b) { b1 = bil2_eval(mb1, TU, TV); b2 = bil2_eval(mb2, TU, TV); }
+                    aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp3, ff3, fa3);
+                } else {
+                    cdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq;
+                }
                 suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw); sw = fw + h;
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
                 const f32x2 eUV = mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 eduv = mul2(bil2_eval(tri2_at(qxy, bc2(sw)), TU, TV), bc2(hq));
-                const T edw = bil_eval<float>(tri_at<float>(qz, sw), lo2(suv), hi2(suv)) * hq, es = hq;
+                T edw, es = hq;
+                if (AUX) {
+                    const f32x2 FW = bc2(sw);
+                    const f32x2 gzw = bil2_eval(tri2_at(qzw, FW), TU, TV);
+                    edw = lo2(gzw) * hq;
+                    f32x2 b1 = 0, b2 = 0;
+                    if (has_b) { b1 = bil2_eval(tri2_at(bxy, FW), TU, TV); b2 = bil2_eval(tri2_at(bzk, FW), TU, TV); }
+                    aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp4, ff4, fa4);
+                } else {
+                    edw = bil_eval<float>(tri_at<float>(qz, sw), lo2(suv), hi2(suv)) * hq;
+                }
                 const T h6 = h * T(1.0 / 6.0);
                 const f32x2 H6 = bc2(h6), TWO = bc2(2.f);
                 tuv = fma2(H6, add2(add2(aUV, mul2(TWO, add2(bUV, cUV))), eUV), tuv);
                 duv = fma2(H6, add2(add2(aduv, mul2(TWO, add2(bduv, cduv))), eduv), duv);
                 dw = fmaf(h6, adw + 2.f * (bdw + cdw) + edw, dw);
                 if (track_s) s = fmaf(h6, as + 2.f * (bs + cs) + es, s);
+                if (AUX) {                      // Simpson over the four stages, summed in FP64
+                    acc_p += (double)(h6 * (fp1 + 2.f * (fp2 + fp3) + fp4));
+                    if (has_b) {
+                        acc_f += (double)(h6 * (ff1 + 2.f * (ff2 + ff3) + ff4));
+                        acc_a += (double)(h6 * (fa1 + 2.f * (fa2 + fa3) + fa4));
+                    }
+                }
                 if (!(ok && dw > T(TT_MARCH_MIN_DW))) { fast = false; break; }
                 if (cross == 0) {
                     ++steps;
@@ -1131,21 +1216,28 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                             prefetch_l1(p + TT_EVENT_PREFETCH * plane + nu);
                         }
                         tri2_advance(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
-                        tri_advance<float>(qz, n00.z, n10.z, n01.z, n11.z);
+                        if (AUX) tri2_advance(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
+                        else tri_advance<float>(qz, n00.z, n10.z, n01.z, n11.z);
+                        if (has_b) {
+                            pa += plane;
+                            const float4* q1 = pa + plane;
+                            const float4 b00 = __ldg(q1), b10 = __ldg(q1 + 1), b01 = __ldg(q1 + nu), b11 = __ldg(q1 + nu + 1);
+                            tri2_advance(bxy, TT_XY(b00), TT_XY(b10), TT_XY(b01), TT_XY(b11));
+                            tri2_advance(bzk, TT_ZW(b00), TT_ZW(b10), TT_ZW(b01), TT_ZW(b11));
+                        }
                         have_next = false;
                     }
                 } else {
                     fw += h;
                     T tu = lo2(tuv), tv = hi2(tuv);
-                    if (cross == 1) { ++cu; tu -= 1.f; p += 1; } else if (cross == -1) { --cu; tu += 1.f; p -= 1; }
-                    else if (cross == 2) { ++cv; tv -= 1.f; p += nu; } else { --cv; tv += 1.f; p -= nu; }
+                    int dp = 0;
+                    if (cross == 1) { ++cu; tu -= 1.f; dp = 1; } else if (cross == -1) { --cu; tu += 1.f; dp = -1; }
+                    else if (cross == 2) { ++cv; tv -= 1.f; dp = nu; } else { --cv; tv += 1.f; dp = -nu; }
+                    p += dp;
+                    if (has_b) pa += dp;
                     tuv = pk2(tu, tv);
                     if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
-                    float4 c00 = __ldg(p), c10 = __ldg(p + 1), c01 = __ldg(p + nu), c11 = __ldg(p + nu + 1);
-                    const float4* p1 = p + plane;
-                    float4 e00 = __ldg(p1), e10 = __ldg(p1 + 1), e01 = __ldg(p1 + nu), e11 = __ldg(p1 + nu + 1);
-                    tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
-                    tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
+                    load_cell();
                     have_next = false;
                 }
             }
@@ -1171,6 +1263,11 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                     sf[(size_t)A.fa[m] * A.np + ray] = Pf[m] + Vf[m] * t_rest;
                     sf[(size_t)(3 + A.fa[m]) * A.np + ray] = Vf[m];
                 }
+            }
+            if (AUX) {
+                aux_out[0 * A.np + ray] = exp(-0.5 * acc_a);
+                aux_out[1 * A.np + ray] = AX.omega_over_c * acc_p;
+                aux_out[2 * A.np + ray] = AX.verdet_nc * acc_f;
             }
             status[ray] = (uint8_t)TT_RAY_EXIT_FACE;
         }
@@ -1266,10 +1363,10 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     int only_flagged = 0;
     if (variant == 3 && p->dtype == TT_F32) {
         if (p->steps_per_cell == 1)
-            trace_event_kernel_f32x2<true><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+            trace_event_kernel_f32x2<true, false><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
                                                                               sf_dev, ray_steps_dev, status_dev, A);
         else
-            trace_event_kernel_f32x2<false><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+            trace_event_kernel_f32x2<false, false><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
                                                                                sf_dev, ray_steps_dev, status_dev, A);
         int rc2 = launch_check("trace_event_kernel_f32x2");
         if (rc2) return rc2;
@@ -1321,9 +1418,25 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
     const long blocks = (np + block - 1) / block;
     TT_REQUIRE(blocks < (1L << 31), "tt_trace_aux: too many rays for one launch");
     cudaStream_t s = (cudaStream_t)stream;
+    TT_REQUIRE(p->variant >= 0 && p->variant <= 4, "tt_trace_aux: unknown kernel variant %d", p->variant);
+    int only_flagged = 0;
+    if (p->dtype == TT_F32 && status_dev && (p->variant == 0 || p->variant == 3)) {
+        // event marching with the passive quantities on board; the gather kernel then redoes the deferred rays
+        if (p->steps_per_cell == 1)
+            trace_event_kernel_f32x2<true, true><<<(unsigned)blocks, block, 0, s>>>(
+                (const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev, ray_steps_dev, status_dev, A,
+                (const float4*)aux4_dev, aux_out_dev, AX);
+        else
+            trace_event_kernel_f32x2<false, true><<<(unsigned)blocks, block, 0, s>>>(
+                (const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev, ray_steps_dev, status_dev, A,
+                (const float4*)aux4_dev, aux_out_dev, AX);
+        int rc2 = launch_check("trace_event_kernel_f32x2<aux>");
+        if (rc2) return rc2;
+        only_flagged = 1;
+    }
     if (p->dtype == TT_F32)
         trace_kernel<float, 1, true><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
-                                                                         ray_steps_dev, status_dev, A, 0,
+                                                                         ray_steps_dev, status_dev, A, only_flagged,
                                                                          (const float4*)aux4_dev, aux_out_dev, AX);
     else
         trace_kernel<double, 1, true><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
