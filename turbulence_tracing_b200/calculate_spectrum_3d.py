@@ -10,7 +10,6 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import DeviceArray
 
 
 def spectrum_3D_scalar(data, dx, k_bin_num=100):

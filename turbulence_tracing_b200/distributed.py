@@ -21,8 +21,6 @@ from __future__ import annotations
 
 import os
 
-import numpy as np
-
 
 def _dist():
     import torch.distributed as dist

@@ -23,7 +23,7 @@ from time import time
 import numpy as np
 
 from . import _lib
-from ._lib import DeviceArray, TTError
+from ._lib import DeviceArray, TTError   # noqa: F401  (TTError re-exported)
 
 c = 299792458.0                 # scipy.constants.c, particle_tracker.py:119
 _NC_COEFF = 3.14207787e-4       # particle_tracker.py:228

@@ -11,8 +11,6 @@ Rejected rays are NaN in all four rows, as in the reference.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import numpy as np
 
 from . import _lib
