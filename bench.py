@@ -105,11 +105,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_traffic(workload, dtype, variant):
-    """dram bytes per trace launch from the committed ncu capture of this configuration, or None."""
+def measured_traffic(workload, dtype, variant, full=False):
+    """dram bytes per trace launch from the committed ncu capture of this configuration, or None
+    (full=True: the whole ncu summary of that capture)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             e = json.load(f)["entries"].get(f"{workload}/{dtype}/{variant or 3}")
+        if full:
+            return e
         return (e["dram_bytes_per_launch"] / 1e9) if e else None
     except Exception:
         return None
@@ -392,6 +395,7 @@ def run_gpu_arm(args, wl):
                 "frac": achieved / peak, "traffic": measured_traffic(wl, dtype, args.variant) if not args.rays else None,
                 "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/traffic.json)",
                 "algorithmic_gb_per_launch": steps_per_launch * bytes_per_step / 1e9, "peak_source": peak_src,
+                "ncu": measured_traffic(wl, dtype, args.variant, full=True) if not args.rays else None,
                 "kernel_ms": kernel_ms, "ray_steps_per_launch": steps_per_launch,
                 "algorithmic_bytes_per_ray_step": bytes_per_step,
                 "note": "algorithmic bytes (4 stages x 8 corners x 16 B); the corners of a cell are held in registers "
