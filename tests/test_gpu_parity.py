@@ -940,3 +940,25 @@ def test_composed_program_and_pickling(tt, golden):
     sh2 = pickle.loads(pickle.dumps(sh))                 # with rays still attached
     sh2.histogram(); sh.histogram()
     np.testing.assert_array_equal(sh2.H, sh.H)
+
+
+def test_save_output_rays_and_lazy_attributes(tt, tmp_path):
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 21)
+    cube = pt.ElectronCube(x, x, x, verbose=True)
+    cube.test_lens(n_e0=5e25, LR=1e-3)
+    cube.calc_dndr()
+    np.random.seed(1)
+    cube.init_beam(500, 3e-3, 1e-3)
+    rf = cube.solve()                         # prints "Ray trace completed in: ... s" like the reference
+    assert cube.last_solve_seconds > 0
+    fn = str(tmp_path / "rays")
+    cube.save_output_rays(fn)
+    np.testing.assert_array_equal(np.load(fn + ".npy"), np.asarray(rf))
+    assert cube.XX.shape == (21, 21, 21) and cube.ne.shape == (21, 21, 21) and cube.ne_nc.max() <= 1
+    np.testing.assert_allclose(cube.ne, orc.density("lens", x, x, x, n_e0=5e25, LR=1e-3), rtol=1e-12)
+    rf2 = rf * 1.0                            # numpy semantics of the lazy device array
+    assert isinstance(rf2, np.ndarray) and rf2.shape == (4, 500) and len(rf) == 4
+    rf[0:4:2, :] *= 1e3                       # the in-place idiom of example_kitchensink.py:94
+    np.testing.assert_allclose(np.asarray(rf)[0], rf2[0] * 1e3)
+    np.testing.assert_allclose(rf.torch.cpu().numpy(), np.asarray(rf))
