@@ -242,7 +242,12 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
                                                     uint8_t* __restrict__ status, TraceArgs A, int only_flagged,
                                                     const typename GridT<T>::V4* __restrict__ aux4 = nullptr,
                                                     double* __restrict__ aux_out = nullptr, AuxArgs AX = AuxArgs()) {
-    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride loop: one ray per thread in a first pass (grid covers all rays); the second pass behind
+    // the event kernel runs a small grid over the status flags (781 k one-ray CTAs that exit at once
+    // would cost 1.5 ms of block scheduling for 1e8 rays)
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long np32 = (A.np + 31) & ~31L;             // whole warps iterate together (shuffle below)
+    for (long tid = (long)blockIdx.x * blockDim.x + threadIdx.x; tid < np32; tid += stride) {
     unsigned steps = 0;
     bool mine = tid < A.np;
     long ray = 0;
@@ -411,6 +416,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
     }
+    }   // grid-stride loop
 }
 
 // ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at arbitrary points,
@@ -500,9 +506,10 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
         only_flagged = 1;          // second pass: the general kernel on the deferred rays only
         variant = 2;
     }
+    const long blocks2 = only_flagged && blocks > 148 * 32 ? 148 * 32 : blocks;      // second pass: small grid
 #define TT_LAUNCH(TYPE, V4T, VAR)                                                                                 \
-    trace_kernel<TYPE, VAR><<<(unsigned)blocks, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev,    \
-                                                                sf_dev, ray_steps_dev, status_dev, A, only_flagged)
+    trace_kernel<TYPE, VAR><<<(unsigned)blocks2, block, 0, s>>>((const V4T*)grid4_dev, s0_dev, perm_dev, rf_dev,   \
+                                                                 sf_dev, ray_steps_dev, status_dev, A, only_flagged)
     if (p->dtype == TT_F32) { if (variant == 1) TT_LAUNCH(float, float4, 1); else TT_LAUNCH(float, float4, 0); }
     else { if (variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
 #undef TT_LAUNCH
@@ -542,12 +549,13 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
         if (rc2) return rc2;
         only_flagged = 1;
     }
+    const long blocks2 = only_flagged && blocks > 148 * 32 ? 148 * 32 : blocks;
     if (p->dtype == TT_F32)
-        trace_kernel<float, 1, true><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
+        trace_kernel<float, 1, true><<<(unsigned)blocks2, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                                                          ray_steps_dev, status_dev, A, only_flagged,
                                                                          (const float4*)aux4_dev, aux_out_dev, AX);
     else
-        trace_kernel<double, 1, true><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
+        trace_kernel<double, 1, true><<<(unsigned)blocks2, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                                                           ray_steps_dev, status_dev, A, 0,
                                                                           (const double4*)aux4_dev, aux_out_dev, AX);
     return launch_check("trace_kernel<aux>");
