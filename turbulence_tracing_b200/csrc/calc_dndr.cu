@@ -23,6 +23,8 @@ struct DndrArgs {
     int fa[3];         // frame: (u, v, w) -> xyz axis
     double nc, ne_max;
     int third;         // the xyz axis that is neither z nor the u axis
+    // FP32-in / FP32-out path: clip level in density units and -1/2 * (1/h | 1/2h) / nc per axis
+    float clip_f, inv_nc_f, k1_f[3], k2_f[3];
 };
 
 // ne/nc clipped at ne_max.  Multiplying by 1/nc instead of dividing differs from the reference's
@@ -70,13 +72,33 @@ __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ 
             int i3[3];
             i3[2] = iz; i3[ua] = iu; i3[ta] = t;
             const size_t idx = (size_t)i3[0] * sx + (size_t)i3[1] * sy + i3[2];
-            const double c = ne_over_nc(ne, idx, a.inv_nc, a.ne_max);
-            double g[3];
-            g[0] = -0.5 * axis_gradient(ne, idx, sx, i3[0], nx, a.invh[0], a.inv2h[0], c, a.inv_nc, a.ne_max);
-            g[1] = -0.5 * axis_gradient(ne, idx, sy, i3[1], ny, a.invh[1], a.inv2h[1], c, a.inv_nc, a.ne_max);
-            g[2] = -0.5 * axis_gradient(ne, idx, 1, i3[2], nz, a.invh[2], a.inv2h[2], c, a.inv_nc, a.ne_max);
             V4 o;
-            o.x = (TOut)g[F0]; o.y = (TOut)g[F1]; o.z = (TOut)g[F2]; o.w = (TOut)c;
+            if constexpr (sizeof(TIn) == 4 && sizeof(TOut) == 4) {
+                // FP32 cube in, FP32 grid out: the difference of two neighbouring FP32 densities is exact in
+                // FP32 (Sterbenz), so nothing is gained by FP64 here and the conversions would make the
+                // kernel XU-bound; differences first, one multiplication by -1/2 / (h nc) afterwards
+                const float clipv = a.clip_f;
+                auto L = [&](size_t id) { const float v = (float)ne[id]; return v > clipv ? clipv : v; };
+                const float c = L(idx);
+                float g[3];
+                const size_t st[3] = {sx, sy, 1};
+                const int nn[3] = {nx, ny, nz};
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int i = i3[ax];
+                    g[ax] = i == 0 ? (L(idx + st[ax]) - c) * a.k1_f[ax]
+                          : i == nn[ax] - 1 ? (c - L(idx - st[ax])) * a.k1_f[ax]
+                                            : (L(idx + st[ax]) - L(idx - st[ax])) * a.k2_f[ax];
+                }
+                o.x = g[F0]; o.y = g[F1]; o.z = g[F2]; o.w = c * a.inv_nc_f;
+            } else {
+                const double c = ne_over_nc(ne, idx, a.inv_nc, a.ne_max);
+                double g[3];
+                g[0] = -0.5 * axis_gradient(ne, idx, sx, i3[0], nx, a.invh[0], a.inv2h[0], c, a.inv_nc, a.ne_max);
+                g[1] = -0.5 * axis_gradient(ne, idx, sy, i3[1], ny, a.invh[1], a.inv2h[1], c, a.inv_nc, a.ne_max);
+                g[2] = -0.5 * axis_gradient(ne, idx, 1, i3[2], nz, a.invh[2], a.inv2h[2], c, a.inv_nc, a.ne_max);
+                o.x = (TOut)g[F0]; o.y = (TOut)g[F1]; o.z = (TOut)g[F2]; o.w = (TOut)c;
+            }
             tile[r + threadIdx.y][threadIdx.x] = o;
         }
     }
@@ -134,6 +156,12 @@ extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3]
     a.nc = nc;
     a.inv_nc = 1.0 / nc;
     a.ne_max = ne_max;
+    a.clip_f = (float)(ne_max * nc);
+    a.inv_nc_f = (float)(1.0 / nc);
+    for (int i = 0; i < 3; ++i) {
+        a.k1_f[i] = (float)(-0.5 * a.invh[i] / nc);
+        a.k2_f[i] = (float)(-0.5 * a.inv2h[i] / nc);
+    }
     TT_REQUIRE(a.n[a.third] <= 65535, "tt_calc_dndr: axis too long for grid.z");
     cudaStream_t s = (cudaStream_t)stream;
     if (ne_dtype == TT_F32 && grid_dtype == TT_F32) return launch_dndr<float, float>(ne_dev, grid4_dev, a, s);
