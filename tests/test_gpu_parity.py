@@ -962,3 +962,38 @@ def test_save_output_rays_and_lazy_attributes(tt, tmp_path):
     rf[0:4:2, :] *= 1e3                       # the in-place idiom of example_kitchensink.py:94
     np.testing.assert_allclose(np.asarray(rf)[0], rf2[0] * 1e3)
     np.testing.assert_allclose(rf.torch.cpu().numpy(), np.asarray(rf))
+
+
+def test_asymmetric_axes_rays_launched_in_front_of_the_cube(tt):
+    """Axes need not be symmetric: extent = axis.max(), rays launch at -extent.  With z in
+    [-2 mm, 6 mm] the beam starts 4 mm in front of the cube and flies freely to it; all kernels agree, the
+    rays stay on the fast path, and sf is the state at T = sqrt(8) extent / c.  (The reference's adaptive
+    RK45 is not a usable oracle here -- it leaps over the cube, see test_rays_outside_and_edge_cases --
+    so the check is the closed form of the slab.)"""
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 41)
+    z = np.linspace(-2e-3, 6e-3, 33)
+    X = np.broadcast_to(x[:, None, None], (41, 41, 33))
+    ne = 1e25 * (1.0 + 8 * X / 5e-3)
+    out = {}
+    for variant in (1, 3):
+        cube = pt.ElectronCube(x, x, z, dtype="float64", steps_per_cell=4, verbose=False)
+        cube.kernel_variant = variant
+        cube.external_ne(np.ascontiguousarray(ne))
+        cube.calc_dndr()
+        np.random.seed(3)
+        cube.init_beam(2000, 1e-3, 1e-3)
+        assert cube.extent == 6e-3 and np.all(cube.s0[2] == -6e-3)
+        rf = np.asarray(cube.solve(return_status=True))
+        out[variant] = (rf, np.asarray(cube.sf), np.asarray(cube.status))
+    np.testing.assert_allclose(out[3][0], out[1][0], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(out[3][1], out[1][1], rtol=1e-9, atol=1e-11)
+    assert np.all(out[3][2] == 1)                       # event kernel: nobody deferred
+    assert np.all(out[1][2] & 1)
+    # uniform gradient: a_x = -c^2/2 * 8e25/(5e-3 nc) while z is in the cube (8 mm / v_z)
+    s0 = cube.s0
+    nc = orc.critical_density()[1]
+    a = -0.5 * orc.C_LIGHT**2 * 8 * 1e25 / (5e-3 * nc)
+    vx_exit = s0[3] + a * 8e-3 / s0[5]
+    np.testing.assert_allclose(out[3][1][3], vx_exit, rtol=2e-6)
+    np.testing.assert_allclose(out[3][0][1], np.arctan(vx_exit / out[3][1][5]), rtol=1e-9)

@@ -87,10 +87,19 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
             X[k] = (s0[(size_t)A.fa[k] * A.np + ray] - A.o[k]) / A.h[k];
             D[k] = s0[(size_t)(3 + A.fa[k]) * A.np + ray] * (1.0 / kC);
         }
+        // a ray launched in front of the cube (asymmetric axes: the reference launches at -extent whatever
+        // the axis starts at) flies freely to the entry face first; the field is zero out there
+        double s_pre = 0.0;
+        if (X[2] < 0.0 && D[2] > TT_MARCH_MIN_DW) {
+            s_pre = -X[2] * A.h[2] / D[2];
+            X[0] += D[0] / A.h[0] * s_pre;
+            X[1] += D[1] / A.h[1] * s_pre;
+            X[2] = 0.0;
+        }
         bool fast = X[0] >= 0.0 && X[0] <= (double)(nu - 1) && X[1] >= 0.0 && X[1] <= (double)(nv - 1) &&
                     X[2] >= 0.0 && X[2] <= (double)(nw - 1) && D[2] > TT_MARCH_MIN_DW;
         // the path-time cap must be out of reach while marching (d_w > 0.75 throughout)
-        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * A.s_max;
+        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * (A.s_max - s_pre);
         int cu = 0, cv = 0, k = 0;
         T tu = T(0), tv = T(0), fw = T(0);
         if (fast) {
@@ -228,7 +237,7 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
             rf[2 * A.np + ray] = Pv - Vv * tb;
             rf[3 * A.np + ray] = atan(Vv / Vw);
             if (sf) {
-                const double t_rest = (A.s_max - (double)s) / kC;
+                const double t_rest = (A.s_max - s_pre - (double)s) / kC;
                 const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
@@ -330,9 +339,18 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
             X[k] = (s0[(size_t)A.fa[k] * A.np + ray] - A.o[k]) / A.h[k];
             D[k] = s0[(size_t)(3 + A.fa[k]) * A.np + ray] * (1.0 / kC);
         }
+        // a ray launched in front of the cube (asymmetric axes: the reference launches at -extent whatever
+        // the axis starts at) flies freely to the entry face first; the field is zero out there
+        double s_pre = 0.0;
+        if (X[2] < 0.0 && D[2] > TT_MARCH_MIN_DW) {
+            s_pre = -X[2] * A.h[2] / D[2];
+            X[0] += D[0] / A.h[0] * s_pre;
+            X[1] += D[1] / A.h[1] * s_pre;
+            X[2] = 0.0;
+        }
         bool fast = X[0] >= 0.0 && X[0] <= (double)(nu - 1) && X[1] >= 0.0 && X[1] <= (double)(nv - 1) &&
                     X[2] >= 0.0 && X[2] <= (double)(nw - 1) && D[2] > TT_MARCH_MIN_DW;
-        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * A.s_max;
+        fast = fast && ((double)(nw - 1) - X[2]) * A.h[2] <= TT_MARCH_MIN_DW * (A.s_max - s_pre);
         int cu = 0, cv = 0, k = 0;
         T tu0 = 0.f, tv0 = 0.f, fw = 0.f;
         if (fast) {
@@ -547,7 +565,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
             rf[2 * A.np + ray] = Pv - Vv * tb;
             rf[3 * A.np + ray] = atan(Vv / Vw);
             if (sf) {
-                const double t_rest = (A.s_max - (double)s) / kC;
+                const double t_rest = (A.s_max - s_pre - (double)s) / kC;
                 const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
 #pragma unroll
                 for (int m = 0; m < 3; ++m) {
