@@ -161,6 +161,25 @@ def golden_traces():
     save("trace_liner", n=31, s0=cube.s0, rf=rf, sf=sf, extent=cube.extent)
 
 
+# ---------------------------------------------------------------- 129^3 random cube (cube regenerated from the seed)
+def golden_grf129():
+    """k^-11/3 cube at 129^3 from the reference's own generator (np.random.seed(17)); 128 rays traced by the
+    reference at rtol 1e-10 in batches of 32.  Only the rays are stored: the tests rebuild the cube with the
+    oracle's generator from the same seed (bit-identical to the reference's, test_oracle_golden)."""
+    np.random.seed(17)
+    f = quiet(tg.gaussian3D_FFT, 64, lambda k: k ** (-11.0 / 3.0))
+    ne = 1e25 * np.clip(1 + 0.3 * f / f.std(), 0, None)
+    x = axes(129)
+    cube = pt.ElectronCube(x, x, x)
+    cube.external_ne(ne.copy())
+    cube.calc_dndr()
+    np.random.seed(18)
+    cube.init_beam(128, 4e-3, 0.05e-3)
+    rf, sf = tight_trace(cube, 1e-10, 1e-13, 32)
+    save("trace_grf129", s0=cube.s0, rf=rf, sf=sf, extent=cube.extent, seed=17, ne_checksum=float(ne.sum()),
+         rtol=1e-10, atol=1e-13)
+
+
 # ---------------------------------------------------------------- spectrum diagnostic
 def golden_spectrum():
     import calculate_spectrum_3d as cs
@@ -261,6 +280,9 @@ if __name__ == "__main__":
     if "--c1" in sys.argv:
         golden_c1()
         sys.exit(0)
+    if "--grf129" in sys.argv:
+        golden_grf129()
+        sys.exit(0)
     if "--spectrum" in sys.argv:
         golden_spectrum()
         sys.exit(0)
@@ -271,3 +293,4 @@ if __name__ == "__main__":
     golden_traces()
     golden_c1()
     golden_spectrum()
+    golden_grf129()

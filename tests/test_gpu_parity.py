@@ -997,3 +997,27 @@ def test_asymmetric_axes_rays_launched_in_front_of_the_cube(tt):
     vx_exit = s0[3] + a * 8e-3 / s0[5]
     np.testing.assert_allclose(out[3][1][3], vx_exit, rtol=2e-6)
     np.testing.assert_allclose(out[3][0][1], np.arctan(vx_exit / out[3][1][5]), rtol=1e-9)
+
+
+def test_trace_grf129_matches_reference(tt, golden):
+    """129^3 k^-11/3 cube (cell size 78 um, 4x the 513^3 cell): 128 rays against the live reference at
+    rtol 1e-10.  The cube is rebuilt from the numpy seed with the oracle's generator (bit-identical to the
+    reference's gaussian3D_FFT), only the rays are stored."""
+    g = golden("trace_grf129")
+    pt = tt.particle_tracker
+    np.random.seed(int(g["seed"]))
+    f = orc.gaussian_fft(64, lambda k: k ** (-11.0 / 3.0))
+    ne = 1e25 * np.clip(1 + 0.3 * f / f.std(), 0, None)
+    assert ne.sum() == float(g["ne_checksum"])
+    x = np.linspace(-5e-3, 5e-3, 129)
+    for dtype, spc, ptol, atol in (("float64", 4, 1e-5 * 4e-3, 1e-5), ("float32", 1, 1e-3 * PIXEL_M, 1e-4)):
+        cube = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=spc, verbose=False)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        cube.s0 = g["s0"]
+        cube.extent = float(g["extent"])
+        rf = np.asarray(cube.solve())
+        pos, ang = _errors(rf, g["rf"], g["s0"], 2)
+        print(f"grf129 {dtype} spc={spc}: pos err {pos:.2e} m = {pos / PIXEL_M:.1e} pixel, angle err {ang:.1e} of rms "
+              f"({np.sqrt(np.mean(g['rf'][1] ** 2 + g['rf'][3] ** 2)) * 1e3:.2f} mrad)")
+        assert pos <= ptol and ang <= atol

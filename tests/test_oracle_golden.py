@@ -163,3 +163,17 @@ def test_spectrum_matches_reference(golden):
     k, s = orc.spectrum_3d_scalar(g["d"], 0.5, 16)
     np.testing.assert_allclose(k, g["k_b"], rtol=1e-14)
     np.testing.assert_allclose(s, g["s_b"], rtol=1e-12, equal_nan=True)
+
+
+def test_grf129_cube_and_first_batch(golden):
+    """the 129^3 fixture: the cube regenerated from the seed is the reference's, and the oracle reproduces
+    the reference's tight-tolerance trace of the first batch of 32 rays"""
+    g = golden("trace_grf129")
+    np.random.seed(int(g["seed"]))
+    f = orc.gaussian_fft(64, lambda k: k ** (-11.0 / 3.0))
+    ne = 1e25 * np.clip(1 + 0.3 * f / f.std(), 0, None)
+    assert ne.sum() == float(g["ne_checksum"])
+    x = np.linspace(-5e-3, 5e-3, 129)
+    field = orc.make_field(ne, x, x, x)
+    rf, sf, _ = orc.solve(field, g["s0"][:, :32], float(g["extent"]), "z", rtol=1e-10, atol=1e-13, batch=32)
+    np.testing.assert_allclose(rf, g["rf"][:, :32], rtol=1e-12, atol=1e-18)
