@@ -26,8 +26,8 @@ Bvec = np.zeros((M, M, M, 3))
 Bvec[..., 1] = 10.0                           # 10 T along the probing direction
 Bvec[..., 0] = 2.0 * tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=2)
 
-test = pt.ElectronCube.legacy(ax, ax, ax, ne_extent, B_on=True, inv_brems=False, phaseshift=True,
-                              probing_direction="y")
+test = pt.ElectronCube(ax, ax, ax, ne_extent, B_on=True, inv_brems=False, phaseshift=True,
+                       probing_direction="y")                 # the call of example_kitchensink.py:72, verbatim
 test.external_ne(rnec)
 test.external_B(Bvec)
 test.calc_dndr()

@@ -141,6 +141,13 @@ def test_axis_validation():
     cube = pt.ElectronCube(x, x, x, probing_direction="q")
     with pytest.raises(ValueError):
         _ = cube._par
+    # both call styles: current reference (direction 4th) and the examples' older one (extent 4th)
+    assert pt.ElectronCube(x, x, x, "y").probing_direction == "y"
+    assert pt.ElectronCube(x, x, x).probing_direction == "z"
+    c = pt.ElectronCube(x, x, x, 1e-3, B_on=True, inv_brems=False, phaseshift=True, probing_direction="x")
+    assert c.probing_direction == "x" and c.B_on and c.phaseshift and c.extent_x == 1e-3
+    with pytest.raises(TypeError):
+        pt.ElectronCube(x, x, x, "y", probing_direction="z")
 
 
 def test_detector_programs_follow_the_reference_sequences():

@@ -64,16 +64,25 @@ class _GradInterp:
 class ElectronCube:
     """A class to hold and generate electron density cubes (particle_tracker.py:121-145)."""
 
-    def __init__(self, x, y, z, probing_direction="z", *, B_on=False, inv_brems=False, phaseshift=False,
+    def __init__(self, x, y, z, *args, probing_direction=None, B_on=False, inv_brems=False, phaseshift=False,
                  dtype="float32", steps_per_cell=1, sort_rays=True, keep_sf=True, verbose=True):
-        """x, y, z: 1-D coordinate arrays (m); probing_direction 'x' | 'y' | 'z' (:125-145).
+        """x, y, z: 1-D coordinate arrays (m); probing_direction 'x' | 'y' | 'z' (4th positional argument or
+        keyword, default 'z'; :125-145).
 
         The reference's example scripts call an older signature ``ElectronCube(x, y, z, extent, B_on=,
-        inv_brems=, phaseshift=, probing_direction=)`` (example_kitchensink.py:72): a number in the
-        4th position is accepted as that ``extent`` (it is implied by the axes and only checked)."""
-        if not isinstance(probing_direction, str):
-            raise TypeError("the 4th positional argument must be the probing direction; pass the old-style "
-                            "extent as ElectronCube.legacy(x, y, z, extent, ...)")
+        inv_brems=, phaseshift=, probing_direction=)`` (example_kitchensink.py:72): a number in the 4th
+        position is accepted as that ``extent`` (it is implied by the axes: ``extent = axis.max()``)."""
+        for a in args:
+            if isinstance(a, str):
+                if probing_direction is not None:
+                    raise TypeError("probing_direction given twice")
+                probing_direction = a
+            elif not isinstance(a, (int, float, np.integer, np.floating)):
+                raise TypeError("ElectronCube(x, y, z[, probing_direction | extent], ...)")
+        if len(args) > 1:
+            raise TypeError("ElectronCube takes at most 4 positional arguments")
+        if probing_direction is None:
+            probing_direction = "z"
         self.z, self.y, self.x = z, y, x
         self.extent_x = x.max()
         self.extent_y = y.max()
@@ -99,7 +108,7 @@ class ElectronCube:
     @classmethod
     def legacy(cls, x, y, z, extent, **kw):
         """Old call style of the example scripts: ElectronCube(x, y, z, extent, B_on=..., ...)."""
-        return cls(x, y, z, kw.pop("probing_direction", "z"), **kw)
+        return cls(x, y, z, extent, **kw)
 
     # ---- geometry -------------------------------------------------------------------------------
     @property
