@@ -197,3 +197,34 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "ray-steps/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_device_array_numpy_semantics_on_cpu_tensor():
+    """DeviceArray only needs a torch tensor: the lazy numpy view, slicing, in-place slices and arithmetic
+    behave like the reference's numpy arrays (exercised here with a CPU tensor)."""
+    import torch
+    from turbulence_tracing_b200 import DeviceArray
+    t = torch.arange(12, dtype=torch.float64).reshape(4, 3)
+    a = DeviceArray(t)
+    assert a.shape == (4, 3) and a.ndim == 2 and a.size == 12 and len(a) == 4 and a.dtype == np.float64
+    np.testing.assert_array_equal(np.asarray(a), np.arange(12.0).reshape(4, 3))
+    np.testing.assert_array_equal(a[1], [3.0, 4.0, 5.0])
+    a[0:4:2, :] *= 1e3                                # the idiom of example_kitchensink.py:94
+    assert a.torch[2, 1].item() == 7000.0 and np.asarray(a)[0, 2] == 2000.0
+    assert isinstance(a * 2, np.ndarray) and (2 * a)[1, 1] == 8.0 and (a - a).sum() == 0 and (-a)[1, 0] == -3.0
+    assert a.T.shape == (3, 4) and a.max() == 8000.0 and a.perm is None
+    assert "DeviceArray" in repr(a)
+
+
+def test_optics_program_composition():
+    from turbulence_tracing_b200 import ray_transfer_matrix as rtm, _lib
+    p0 = rtm.OpticsProgram()
+    p1 = p0.distance(10).sym_lens(5)
+    p2 = p1.angular_filter([0, 1, 2, 3]).knife_edge(0.5, "x", -1)
+    assert len(p0) == 0 and len(p1) == 2 and len(p2) == 5          # immutable builder
+    assert p2.ops[0] == (_lib.OP_DISTANCE, 10.0, 0.0) and p2.ops[1] == (_lib.OP_LENS, 5.0, 5.0)
+    assert p2.ops[2] == (_lib.OP_ANNULAR_STOP, 0.0, 1.0) and p2.ops[3] == (_lib.OP_ANNULAR_STOP, 2.0, 3.0)
+    assert p2.ops[4] == (_lib.OP_KNIFE_EDGE, 0.5, -1.0)
+    assert rtm.OpticsProgram().knife_edge(0.0, "y", 1).ops[0][2] == 2.0
+    with pytest.raises(ValueError):
+        rtm.OpticsProgram().knife_edge(0.0, "z", 1)
