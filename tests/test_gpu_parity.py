@@ -1021,3 +1021,21 @@ def test_trace_grf129_matches_reference(tt, golden):
         print(f"grf129 {dtype} spc={spc}: pos err {pos:.2e} m = {pos / PIXEL_M:.1e} pixel, angle err {ang:.1e} of rms "
               f"({np.sqrt(np.mean(g['rf'][1] ** 2 + g['rf'][3] ** 2)) * 1e3:.2f} mrad)")
         assert pos <= ptol and ang <= atol
+
+
+def test_calc_dndr_fp32_streaming_kernel_all_directions(tt):
+    """FP32 cube -> FP32 grid takes the 2.5-D streaming stencil kernel: all probing directions, sizes that
+    are not multiples of the 32-voxel tiles or of the 32-plane chunks, values above the clip."""
+    pt = tt.particle_tracker
+    rng = np.random.RandomState(9)
+    x, y, z = np.linspace(-3e-3, 3e-3, 45), np.linspace(-2e-3, 2e-3, 70), np.linspace(-4e-3, 4e-3, 37)
+    ne = (1.2e27 * rng.rand(45, 70, 37)).astype(np.float32)
+    ref = orc.calc_dndr(ne.astype(np.float64), x, y, z, 1053e-9, 0.7)
+    for d in "xyz":
+        cube = pt.ElectronCube(x, y, z, d, dtype="float32")
+        cube.external_ne(ne)
+        cube.calc_dndr(ne_max=0.7)
+        assert abs(cube.ne_nc.max() - 0.7) < 1e-7
+        for name in ("ne_nc", "dndx", "dndy", "dndz"):
+            np.testing.assert_allclose(getattr(cube, name), ref[name], rtol=0, atol=3e-7 * np.abs(ref[name]).max(),
+                                       err_msg=f"{name} direction {d}")
