@@ -118,92 +118,12 @@ __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ 
     }
 }
 
-// ---- FP32 cube -> FP32 grid: 2.5-D streaming stencil ----------------------------------------------------
-// A CTA owns a 32 (z) x 32 (u) column and marches along the third axis t, keeping the planes t-1, t, t+1
-// (with a one-voxel halo in z and u, densities already clipped) in a ring of shared-memory tiles: every
-// input voxel is read from global memory ~1.1 times instead of 7, the four outputs per thread go through
-// the transposing float4 tile as in the kernel above.  Same arithmetic as its FP32 branch.
-static constexpr int kTch = 32;        // planes per CTA along t (two extra plane loads per chunk)
-
-template <int PAR>
-__global__ void __launch_bounds__(256) calc_dndr_stream_kernel(const float* __restrict__ ne, float4* __restrict__ grid,
-                                                               DndrArgs a) {
-    constexpr int F0 = PAR == 0 ? 1 : 0, F1 = PAR == 2 ? 1 : 2, F2 = PAR;
-    constexpr int ua = F0, ta = 1 - F0;
-    __shared__ float in[3][34][35];
-    __shared__ float4 tile[32][33];
-    const int z0 = blockIdx.x * 32, u0 = blockIdx.y * 32;
-    const int t_begin = blockIdx.z * kTch, nt = a.n[ta], nu = a.n[ua], nz = a.n[2];
-    const int t_end = min(t_begin + kTch, nt);
-    const size_t stride[3] = {(size_t)a.n[1] * a.n[2], (size_t)a.n[2], 1};
-    const size_t su = stride[ua], st = stride[ta];
-    const float clipv = a.clip_f;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-
-    auto load_plane = [&](int t, int slot) {          // plane t (clamped into the cube) -> in[slot]
-        const int tc = min(max(t, 0), nt - 1);
-        for (int e = tid; e < 34 * 34; e += 256) {
-            const int lu = e / 34, lz = e % 34;
-            const int u = min(max(u0 - 1 + lu, 0), nu - 1), z = min(max(z0 - 1 + lz, 0), nz - 1);
-            const float v = __ldg(ne + (size_t)u * su + (size_t)tc * st + z);
-            in[slot][lu][lz] = v > clipv ? clipv : v;
-        }
-    };
-    load_plane(t_begin - 1, 0);
-    load_plane(t_begin, 1);
-    int prev = 0, cur = 1, next = 2;
-    const int ou = u0 + threadIdx.x, nv = a.n[F1];
-    for (int t = t_begin; t < t_end; ++t) {
-        load_plane(t + 1, next);
-        __syncthreads();
-        const int iz = z0 + threadIdx.x, lz = threadIdx.x + 1;
-#pragma unroll
-        for (int r = 0; r < 32; r += 8) {
-            const int lu = r + threadIdx.y + 1, iu = u0 + r + threadIdx.y;
-            if (iz < nz && iu < nu) {
-                const float c = in[cur][lu][lz];
-                float g[3];
-                g[ua] = iu == 0 ? (in[cur][lu + 1][lz] - c) * a.k1_f[ua]
-                      : iu == nu - 1 ? (c - in[cur][lu - 1][lz]) * a.k1_f[ua]
-                                     : (in[cur][lu + 1][lz] - in[cur][lu - 1][lz]) * a.k2_f[ua];
-                g[2] = iz == 0 ? (in[cur][lu][lz + 1] - c) * a.k1_f[2]
-                     : iz == nz - 1 ? (c - in[cur][lu][lz - 1]) * a.k1_f[2]
-                                    : (in[cur][lu][lz + 1] - in[cur][lu][lz - 1]) * a.k2_f[2];
-                g[ta] = t == 0 ? (in[next][lu][lz] - c) * a.k1_f[ta]
-                      : t == nt - 1 ? (c - in[prev][lu][lz]) * a.k1_f[ta]
-                                    : (in[next][lu][lz] - in[prev][lu][lz]) * a.k2_f[ta];
-                tile[r + threadIdx.y][threadIdx.x] = make_float4(g[F0], g[F1], g[F2], c * a.inv_nc_f);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 32; r += 8) {
-            const int oz = z0 + r + threadIdx.y;
-            if (ou < nu && oz < nz) {
-                int i3[3];
-                i3[2] = oz; i3[ua] = ou; i3[ta] = t;
-                grid[((size_t)i3[F2] * nv + i3[F1]) * nu + ou] = tile[threadIdx.x][r + threadIdx.y];
-            }
-        }
-        const int tmp = prev; prev = cur; cur = next; next = tmp;
-        // (the next iteration's load_plane writes the slot that was `prev`: every thread is past the
-        //  compute phase that read it, because of the barrier above)
-    }
-}
-
 template <typename TIn, typename TOut>
 static int launch_dndr(const void* ne, void* grid, const DndrArgs& a, cudaStream_t s) {
     dim3 block(32, 8);
     dim3 gridDim((a.n[2] + 31) / 32, (a.n[a.fa[0]] + 31) / 32, a.n[a.third]);
     typedef typename Vec4<TOut>::type V4;
     const int par = a.fa[2];
-    if constexpr (sizeof(TIn) == 4 && sizeof(TOut) == 4) {
-        dim3 g2((a.n[2] + 31) / 32, (a.n[a.fa[0]] + 31) / 32, (a.n[a.third] + kTch - 1) / kTch);
-        if (par == 0) calc_dndr_stream_kernel<0><<<g2, block, 0, s>>>((const float*)ne, (float4*)grid, a);
-        else if (par == 1) calc_dndr_stream_kernel<1><<<g2, block, 0, s>>>((const float*)ne, (float4*)grid, a);
-        else calc_dndr_stream_kernel<2><<<g2, block, 0, s>>>((const float*)ne, (float4*)grid, a);
-        return launch_check("calc_dndr_stream_kernel");
-    }
     if (par == 0) calc_dndr_kernel<TIn, TOut, 0><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
     else if (par == 1) calc_dndr_kernel<TIn, TOut, 1><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
     else calc_dndr_kernel<TIn, TOut, 2><<<gridDim, block, 0, s>>>((const TIn*)ne, (V4*)grid, a);
