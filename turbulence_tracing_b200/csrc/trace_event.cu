@@ -318,7 +318,8 @@ __device__ __forceinline__ void aux_integrands(float nn, f32x2 bxy, f32x2 bzk, f
     }
 }
 
-template <bool SPC1, bool AUX>
+// CUBIC: h_u = h_v = h_w, so the index-space slopes need no rescaling (x * 1.0f is exact: same bits).
+template <bool SPC1, bool AUX, bool CUBIC>
 __global__ void __launch_bounds__(128, AUX ? 3 : TT_EVENT_MIN_BLOCKS)
 trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
                          const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
@@ -406,7 +407,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 T q = trcp<T>(dw), hq = hw * q;
                 bool ok = dw > T(TT_MARCH_MIN_DW);
                 f32x2 TU = bc2(lo2(tuv)), TV = bc2(hi2(tuv));
-                const f32x2 aUV = mul2(mul2(RUV, duv), bc2(q));
+                const f32x2 aUV = CUBIC ? mul2(duv, bc2(q)) : mul2(mul2(RUV, duv), bc2(q));
                 const f32x2 aduv = mul2(bil2_eval(tri2_at(qxy, bc2(fw)), TU, TV), bc2(hq));
                 T adw, as = hq;
                 float fp1 = 0.f, ff1 = 0.f, fa1 = 0.f, fp2 = 0.f, ff2 = 0.f, fa2 = 0.f, fp3 = 0.f, ff3 = 0.f, fa3 = 0.f,
@@ -456,7 +457,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 } else {
                     mz = tri_at<float>(qz, sw);
                 }
-                const f32x2 bUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 bUV = CUBIC ? mul2(duv2, bc2(q)) : mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 bduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
                 T bdw, bs = hq;
                 if (AUX) {
@@ -471,7 +472,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
-                const f32x2 cUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 cUV = CUBIC ? mul2(duv2, bc2(q)) : mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 cduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
                 T cdw, cs = hq;
                 if (AUX) {
@@ -486,7 +487,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
                 suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw); sw = fw + h;
                 q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
                 TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
-                const f32x2 eUV = mul2(mul2(RUV, duv2), bc2(q));
+                const f32x2 eUV = CUBIC ? mul2(duv2, bc2(q)) : mul2(mul2(RUV, duv2), bc2(q));
                 const f32x2 eduv = mul2(bil2_eval(tri2_at(qxy, bc2(sw)), TU, TV), bc2(hq));
                 T edw, es = hq;
                 if (AUX) {
@@ -598,16 +599,23 @@ int launch_trace_event(int dtype, bool packed, int steps_per_cell, const void* g
     const int block = 128;
     const unsigned blocks = (unsigned)((A.np + block - 1) / block);
     const bool spc1 = steps_per_cell == 1;
+    const bool cubic = A.ruf == 1.0f && A.rvf == 1.0f;
+#define TT_EV2(S1, AX_, CU, ...) trace_event_kernel_f32x2<S1, AX_, CU><<<blocks, block, 0, s>>>(__VA_ARGS__)
+#define TT_EV2_DISPATCH(AX_, ...)                                                       \
+    do {                                                                                \
+        if (spc1) { if (cubic) TT_EV2(true, AX_, true, __VA_ARGS__); else TT_EV2(true, AX_, false, __VA_ARGS__); }   \
+        else { if (cubic) TT_EV2(false, AX_, true, __VA_ARGS__); else TT_EV2(false, AX_, false, __VA_ARGS__); }      \
+    } while (0)
     if (dtype == TT_F32 && aux_out) {
-        if (spc1) trace_event_kernel_f32x2<true, true><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A, (const float4*)aux4, aux_out, AX);
-        else trace_event_kernel_f32x2<false, true><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A, (const float4*)aux4, aux_out, AX);
+        TT_EV2_DISPATCH(true, (const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A, (const float4*)aux4, aux_out, AX);
         return launch_check("trace_event_kernel_f32x2<aux>");
     }
     if (dtype == TT_F32 && packed) {
-        if (spc1) trace_event_kernel_f32x2<true, false><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
-        else trace_event_kernel_f32x2<false, false><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
+        TT_EV2_DISPATCH(false, (const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
         return launch_check("trace_event_kernel_f32x2");
     }
+#undef TT_EV2_DISPATCH
+#undef TT_EV2
     if (dtype == TT_F32) {
         if (spc1) trace_event_kernel<float, true><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
         else trace_event_kernel<float, false><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
