@@ -379,7 +379,7 @@ def run_gpu_arm(args, wl):
             _ = cube2.ray_steps                     # D2H of the counter
             return H, cube2._steps_dev
 
-        ms2, tot2, _, _ = timed(step_e2e, cube2, 1, args.steps)
+        ms2, tot2, _, _ = timed(step_e2e, cube2, 2, args.steps)
         e2e = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / args.steps,
                "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
                "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
     // grid-stride loop: one ray per thread in a first pass (grid covers all rays); the second pass behind
     // the event kernel runs a small grid over the status flags (781 k one-ray CTAs that exit at once
     // would cost 1.5 ms of block scheduling for 1e8 rays)
+    if (only_flagged && A.any_deferred && *A.any_deferred == 0u) return;   // nothing was deferred
     const long stride = (long)gridDim.x * blockDim.x;
     const long np32 = (A.np + 31) & ~31L;             // whole warps iterate together (shuffle below)
     for (long tid = (long)blockIdx.x * blockDim.x + threadIdx.x; tid < np32; tid += stride) {
@@ -464,6 +465,7 @@ static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3
         TT_REQUIRE(A.n[k] >= 2, "every axis needs >= 2 points");
         TT_REQUIRE(A.h[k] > 0, "spacing must be > 0");
     }
+    A.any_deferred = nullptr;
     A.plane_elems = (long long)A.n[0] * A.n[1];
     A.hwf = (float)A.h[2]; A.ruf = (float)(A.h[2] / A.h[0]); A.rvf = (float)(A.h[2] / A.h[1]);
     return TT_OK;
@@ -498,7 +500,16 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     TT_REQUIRE(variant < 3 || status_dev, "tt_trace: event marching (variant 3/4) needs status_dev");
     if (variant == 0) variant = status_dev ? 3 : 2;
     int only_flagged = 0;
+    unsigned int* flag = nullptr;
     if (variant >= 3) {
+        // stream-ordered 4-byte scratch flag: "did the event kernel defer any ray?"
+        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
+            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+            A.any_deferred = flag;
+        } else {
+            (void)cudaGetLastError();
+            flag = nullptr;
+        }
         // event marching (packed FP32x2 arithmetic for variant 3 in FP32), then the second pass below
         int rc2 = launch_trace_event(p->dtype, variant == 3, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, nullptr, nullptr, AuxArgs(), s);
@@ -513,6 +524,7 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     if (p->dtype == TT_F32) { if (variant == 1) TT_LAUNCH(float, float4, 1); else TT_LAUNCH(float, float4, 0); }
     else { if (variant == 1) TT_LAUNCH(double, double4, 1); else TT_LAUNCH(double, double4, 0); }
 #undef TT_LAUNCH
+    if (flag) cudaFreeAsync(flag, s);
     return launch_check("trace_kernel");
 }
 
@@ -542,7 +554,15 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
     cudaStream_t s = (cudaStream_t)stream;
     TT_REQUIRE(p->variant >= 0 && p->variant <= 4, "tt_trace_aux: unknown kernel variant %d", p->variant);
     int only_flagged = 0;
+    unsigned int* flag = nullptr;
     if (p->dtype == TT_F32 && status_dev && (p->variant == 0 || p->variant == 3)) {
+        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
+            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+            A.any_deferred = flag;
+        } else {
+            (void)cudaGetLastError();
+            flag = nullptr;
+        }
         // event marching with the passive quantities on board; the gather kernel then redoes the deferred rays
         int rc2 = launch_trace_event(TT_F32, true, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, aux4_dev, aux_out_dev, AX, s);
@@ -558,6 +578,7 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
         trace_kernel<double, 1, true><<<(unsigned)blocks2, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                                                           ray_steps_dev, status_dev, A, 0,
                                                                           (const double4*)aux4_dev, aux_out_dev, AX);
+    if (flag) cudaFreeAsync(flag, s);
     return launch_check("trace_kernel<aux>");
 }
 

@@ -24,6 +24,8 @@ struct TraceArgs {
     // multiplies, no double->float conversions)
     long long plane_elems;   // nu * nv
     float hwf, ruf, rvf;     // (float) h_w, h_w/h_u, h_w/h_v
+    unsigned int* any_deferred;   // device flag (nullable): set by an event kernel that deferred a ray, so
+                                  // that the second pass can return at once when there is nothing to do
 };
 
 template <typename T> struct GridT;

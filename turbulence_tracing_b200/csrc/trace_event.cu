@@ -224,6 +224,7 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
         }
         if (!fast) {
             status[ray] = TT_RAY_DEFERRED;          // the general kernel redoes this ray from s0
+            if (A.any_deferred) *A.any_deferred = 1u;   // (benign race: everybody stores 1)
             steps = 0;
         } else {
             // ---- epilogue: ray_at_exit (particle_tracker.py:345-380) and state at time T ---------
@@ -554,6 +555,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
         }
         if (!fast) {
             status[ray] = TT_RAY_DEFERRED;
+            if (A.any_deferred) *A.any_deferred = 1u;
             steps = 0;
         } else {
             const double Pu = A.o[0] + ((double)cu + (double)lo2(tuv)) * A.h[0];
