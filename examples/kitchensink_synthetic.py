@@ -1,11 +1,13 @@
 """The reference's example_kitchensink.py flow (particle_tracking/example_kitchensink.py:38-134) on the
-B200 backend, with synthetic data instead of the (missing) .pvti simulation files: ne + B cubes, probing
-along y, phase + Faraday rotation, amplitude- and polarisation-weighted detector images.
+B200 backend, with synthetic data instead of the (missing) simulation files: ne + B cubes are written as
+.pvti files and read back with ``pvti_readin`` like the example does (:7-36, no vtk needed), probing along
+y, phase + Faraday rotation, amplitude- and polarisation-weighted detector images.
 
     python examples/kitchensink_synthetic.py [Np]
 """
 import os
 import sys
+import tempfile
 
 import numpy as np
 
@@ -13,12 +15,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turbulence_tracing_b200 import particle_tracker as pt      # noqa: E402
 from turbulence_tracing_b200 import ray_transfer_matrix as rtm  # noqa: E402
 from turbulence_tracing_b200 import turboGen as tg              # noqa: E402
+from turbulence_tracing_b200.io import pvti_readin, write_pvti, centred_axes   # noqa: E402
 
 Np = int(float(sys.argv[1])) if len(sys.argv) > 1 else int(1e5)
 N = 32                                        # cube of (2N+1)^3 = 65^3 points
 M = 2 * N + 1
 ne_extent = 5e-3
-ax = np.linspace(-ne_extent, ne_extent, M)
 
 f = tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=1)
 rnec = 1e25 * np.clip(1 + 0.3 * f / f.std(), 0, None)
@@ -26,7 +28,18 @@ Bvec = np.zeros((M, M, M, 3))
 Bvec[..., 1] = 10.0                           # 10 T along the probing direction
 Bvec[..., 0] = 2.0 * tg.gaussian3D_FFT(N, lambda k: k ** (-11.0 / 3.0), seed=2)
 
-test = pt.ElectronCube(ax, ax, ax, ne_extent, B_on=True, inv_brems=False, phaseshift=True,
+
+# "simulation output" on disk, then the example's loading step (example_kitchensink.py:43-62)
+with tempfile.TemporaryDirectory() as d:
+    h = 2 * ne_extent / (M - 1)
+    write_pvti(os.path.join(d, "x08_rnec-400.pvti"), rnec, spacing=(h, h, h), name="rnec", pieces=(2, 2, 1), compress=True)
+    write_pvti(os.path.join(d, "x08_Bvec-400.pvti"), Bvec, spacing=(h, h, h), name="Bvec", pieces=(2, 1, 1))
+    rnec, dim, spacing = pvti_readin(os.path.join(d, "x08_rnec-400.pvti"))
+    Bvec, dim, spacing = pvti_readin(os.path.join(d, "x08_Bvec-400.pvti"))
+ne_x, ne_y, ne_z = centred_axes(dim, spacing)
+assert ne_y[-1] == ne_extent or abs(ne_y[-1] - ne_extent) < 1e-15
+
+test = pt.ElectronCube(ne_x, ne_y, ne_z, ne_extent, B_on=True, inv_brems=False, phaseshift=True,
                        probing_direction="y")                 # the call of example_kitchensink.py:72, verbatim
 test.external_ne(rnec)
 test.external_B(Bvec)

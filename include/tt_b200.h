@@ -134,6 +134,25 @@ int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* g
                  double* rf_dev, double* sf_dev, double* aux_out_dev,
                  unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
 
+/* ---- rectilinear grids: axes whose nodes are NOT equally spaced ------------------------------------
+ * The reference takes any ascending coordinate arrays: numpy.gradient(ne_nc, x, axis=0) uses the
+ * non-uniform second-order stencil and RegularGridInterpolator((x, y, z), ...) locates cells by
+ * bisection (particle_tracker.py:235-241).  These entry points are the same three operations with the
+ * node coordinates x_dev[nx], y_dev[ny], z_dev[nz] (device, FP64, strictly ascending) instead of
+ * origin + spacing; grid layout, outputs, status flags and ray order are those of tt_calc_dndr /
+ * tt_trace / tt_dndr.  tt_trace_axes ignores p->origin_xyz, p->spacing_xyz and p->variant; its
+ * arithmetic is FP64 whatever the grid's element type (general-geometry path, not the speed path). */
+int tt_calc_dndr_axes(const void* ne_dev, int ne_dtype, const int n_xyz[3], const double* x_dev,
+                      const double* y_dev, const double* z_dev, int par, double nc, double ne_max,
+                      void* grid4_dev, int grid_dtype, tt_stream_t stream);
+int tt_trace_axes(const tt_trace_params* p, const double* x_dev, const double* y_dev, const double* z_dev,
+                  const void* grid4_dev, const double* s0_dev, long np, const uint32_t* perm_dev,
+                  double* rf_dev, double* sf_dev, unsigned long long* ray_steps_dev, uint8_t* status_dev,
+                  tt_stream_t stream);
+int tt_dndr_axes(const void* grid4_dev, int grid_dtype, const int n_xyz[3], const double* x_dev,
+                 const double* y_dev, const double* z_dev, int par, const double* pos_dev, long npts,
+                 double* out_dev, tt_stream_t stream);
+
 /* ---- K5+K6: ray_transfer_matrix.py optics (:37-154), detector programs (:208-299) and
  *      Rays.histogram (:173-195) ---------------------------------------------------------------
  * One pass over the rays: scale positions (pos_scale = 1e3 is m_to_mm, :37-40), run the element

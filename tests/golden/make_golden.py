@@ -161,6 +161,49 @@ def golden_traces():
     save("trace_liner", n=31, s0=cube.s0, rf=rf, sf=sf, extent=cube.extent)
 
 
+# ---------------------------------------------------------------- rectilinear (non-uniformly spaced) axes
+def stretched_axes():
+    """Three differently stretched axes over [-5, 5] mm: tanh clustering towards the centre, geometric growth,
+    and a sinusoidal modulation of the node spacing (ratios of neighbouring cell sizes up to ~1.3)."""
+    ext = 5e-3
+    u = np.linspace(-1, 1, 29)
+    x = ext * np.tanh(1.6 * u) / np.tanh(1.6)
+    w = np.cumsum(np.concatenate([[0.0], 1.07 ** np.arange(32)]))
+    y = ext * (2 * w / w[-1] - 1)
+    v = np.linspace(-1, 1, 37)
+    z = ext * (v + 0.12 * np.sin(2 * np.pi * v) / (2 * np.pi) * 2)
+    for a in (x, y, z):
+        a[0], a[-1] = -ext, ext
+        assert np.all(np.diff(a) > 0)
+    return x, y, z
+
+
+def golden_rectilinear():
+    x, y, z = stretched_axes()
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    rng = np.random.RandomState(21)
+    ne = 2e25 * (1 + 0.5 * np.sin(2 * np.pi * X / 4e-3) * np.cos(2 * np.pi * Y / 3e-3)) * np.exp(-(Z / 3e-3) ** 2)
+    ne *= 1 + 0.05 * rng.rand(*ne.shape)
+    pts = np.stack([rng.uniform(-5.5e-3, 5.5e-3, 200) for _ in range(3)])
+    pts[:, 0] = [x[-1], y[-1], z[-1]]
+    pts[:, 1] = [x[0], y[0], z[0]]
+    pts[:, 2] = [x[7], y[9], z[11]]
+    out = dict(x=x, y=y, z=z, ne=ne, pts=pts)
+    for d, np_, seed in (("z", 64, 31), ("y", 32, 32), ("x", 16, 33)):
+        cube = pt.ElectronCube(x, y, z, probing_direction=d)
+        cube.external_ne(ne.copy())
+        cube.calc_dndr()
+        if d == "z":
+            sub = (slice(None, None, 2),) * 3            # every other node (all three axes are odd: faces included)
+            out.update(dndx_sub=cube.dndx[sub], dndy_sub=cube.dndy[sub], dndz_sub=cube.dndz[sub],
+                       dndr_at_pts=cube.dndr(pts))
+        np.random.seed(seed)
+        cube.init_beam(np_, 4e-3, 2e-3)
+        rf, sf = tight_trace(cube, 1e-10, 1e-13, 32)
+        out.update({f"s0_{d}": cube.s0, f"rf_{d}": rf, f"sf_{d}": sf, f"extent_{d}": cube.extent})
+    save("trace_rectilinear", rtol=1e-10, atol=1e-13, **out)
+
+
 # ---------------------------------------------------------------- 129^3 random cube (cube regenerated from the seed)
 def golden_grf129():
     """k^-11/3 cube at 129^3 from the reference's own generator (np.random.seed(17)); 128 rays traced by the
@@ -283,6 +326,9 @@ if __name__ == "__main__":
     if "--grf129" in sys.argv:
         golden_grf129()
         sys.exit(0)
+    if "--rect" in sys.argv:
+        golden_rectilinear()
+        sys.exit(0)
     if "--spectrum" in sys.argv:
         golden_spectrum()
         sys.exit(0)
@@ -294,3 +340,4 @@ if __name__ == "__main__":
     golden_c1()
     golden_spectrum()
     golden_grf129()
+    golden_rectilinear()

@@ -136,8 +136,15 @@ def test_axis_validation():
     bad[4] += 1e-6
     with pytest.raises(NotImplementedError):
         pt._uniform_spacing(bad, "x")
+    assert pt._axis_spacing(bad, "x")[2] is False and pt._axis_spacing(x, "x")[2] is True
+    assert pt.ElectronCube(x, bad, x)._geometry()[2] is True       # one stretched axis -> rectilinear kernels
+    assert pt.ElectronCube(x, x, x)._geometry()[2] is False
     with pytest.raises(ValueError):
         pt._uniform_spacing(x[::-1], "x")
+    dup = x.copy()
+    dup[3] = dup[2]
+    with pytest.raises(ValueError):
+        pt._axis_spacing(dup, "x")
     cube = pt.ElectronCube(x, x, x, probing_direction="q")
     with pytest.raises(ValueError):
         _ = cube._par

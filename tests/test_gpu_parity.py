@@ -99,15 +99,131 @@ def test_calc_dndr_clip_edges_and_float32_input(tt, golden):
     np.testing.assert_allclose(cube32.dndx, d["dndx"], rtol=0, atol=1e-5 * np.abs(d["dndx"]).max())
 
 
-def test_nonuniform_axis_raises(tt):
+def test_rectilinear_calc_dndr_and_dndr(tt, golden):
+    """Non-uniformly spaced axes: numpy.gradient's non-uniform stencil and the interpolator's bisection
+    (tt_calc_dndr_axes / tt_dndr_axes), against values produced by the live reference."""
+    g = golden("trace_rectilinear")
     pt = tt.particle_tracker
-    x = np.linspace(-1e-3, 1e-3, 9)
-    xb = x.copy()
-    xb[3] += 1e-5
-    cube = pt.ElectronCube(xb, x, x)
-    cube.external_ne(np.zeros((9, 9, 9)))
-    with pytest.raises(NotImplementedError):
+    sub = (slice(None, None, 2),) * 3
+    for dr in "xyz":
+        cube = pt.ElectronCube(g["x"], g["y"], g["z"], probing_direction=dr, dtype="float64", verbose=False)
+        cube.external_ne(g["ne"])
         cube.calc_dndr()
+        assert cube._nodes is not None
+        for name in ("dndx", "dndy", "dndz"):
+            ref = g[name + "_sub"]
+            np.testing.assert_allclose(getattr(cube, name)[sub], ref, rtol=0, atol=1e-11 * np.abs(ref).max(),
+                                       err_msg=f"{name} dir={dr}")
+        got = cube.dndr(g["pts"])
+        ref = g["dndr_at_pts"]
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+        outside = (np.abs(g["pts"]) > 5e-3).any(axis=0)
+        assert outside.any() and np.all(got[:, outside] == 0)
+    cube32 = pt.ElectronCube(g["x"], g["y"], g["z"], dtype="float32", verbose=False)
+    cube32.external_ne(g["ne"].astype(np.float32))
+    cube32.calc_dndr()
+    np.testing.assert_allclose(cube32.dndx[sub], g["dndx_sub"], rtol=0, atol=2e-6 * np.abs(g["dndx_sub"]).max())
+    # a uniform axis set given to the rectilinear entry points gives the uniform kernels' grid
+    x = np.linspace(-5e-3, 5e-3, 17)
+    gu = golden("calc_dndr_uniform")
+    cu = pt.ElectronCube(x, x, x, dtype="float64", verbose=False)
+    cu.external_ne(gu["ne"])
+    old = pt.UNIFORM_RTOL
+    try:
+        pt.UNIFORM_RTOL = -1.0            # force the rectilinear path
+        cu.calc_dndr()
+        assert cu._nodes is not None
+        np.testing.assert_allclose(cu.dndy, gu["dndy"], rtol=0, atol=1e-11 * np.abs(gu["dndy"]).max())
+    finally:
+        pt.UNIFORM_RTOL = old
+
+
+@pytest.mark.parametrize("direction", ["z", "y", "x"])
+def test_rectilinear_trace_matches_reference(tt, golden, direction):
+    """Rays through a cube on stretched axes (cell-size ratios up to 6 along x): FP64 parity bar against the
+    live reference at rtol 1e-10; float32 grid within the FP32 pixel bar; status / ray order / steps."""
+    g = golden("trace_rectilinear")
+    pt = tt.particle_tracker
+    s0, ref = g["s0_" + direction], g["rf_" + direction]
+    par = "xyz".index(direction)
+    beam = np.abs(s0[[a for a in range(3) if a != par]]).max()
+    errs = {}
+    for spc in (2, 8):
+        cube = pt.ElectronCube(g["x"], g["y"], g["z"], probing_direction=direction, dtype="float64",
+                               steps_per_cell=spc, verbose=False)
+        cube.external_ne(g["ne"])
+        cube.calc_dndr()
+        cube.s0 = s0
+        cube.extent = float(g["extent_" + direction])
+        rf = np.asarray(cube.solve())
+        errs[spc] = _errors(rf, ref, s0, par)
+    print(f"rectilinear {direction}: (pos m, angle/rms) by steps_per_cell {errs}")
+    assert errs[8][0] / beam <= 1e-5 and errs[8][1] <= 1e-5
+    assert errs[8][1] <= errs[2][1]
+    sf = np.asarray(cube.sf)
+    np.testing.assert_allclose(sf[:3], g["sf_" + direction][:3], rtol=0, atol=1e-5 * beam)
+    st = np.asarray(cube.status)
+    assert np.all(st & 1)                                     # every ray left through the far face
+    nw = len((g["x"], g["y"], g["z"])[par])
+    # probing 'x' launches on the +extent face (reference quirk, particle_tracker.py:287): the rays leave at once
+    assert cube.ray_steps == (0 if direction == "x" else 8 * (nw - 1) * s0.shape[1])
+    cube.sort_rays = False
+    np.testing.assert_array_equal(np.asarray(cube.solve()), rf)
+    # float32 grid (arithmetic stays FP64 on this path)
+    c32 = pt.ElectronCube(g["x"], g["y"], g["z"], probing_direction=direction, dtype="float32",
+                          steps_per_cell=8, verbose=False)
+    c32.external_ne(g["ne"])
+    c32.calc_dndr()
+    c32.s0 = s0
+    c32.extent = float(g["extent_" + direction])
+    pos32, _ = _errors(np.asarray(c32.solve()), ref, s0, par)
+    print(f"rectilinear {direction} float32 grid: pos err {pos32:.3e} m = {pos32 / PIXEL_M:.2e} pixel")
+    assert pos32 <= 1e-3 * PIXEL_M
+
+
+def test_rectilinear_edge_cases_and_uniform_equivalence(tt):
+    """The rectilinear kernel on a uniform grid reproduces the uniform FP64 kernel; rays outside / missing /
+    side exits / steep rays follow the same rules; the passive quantities refuse loudly."""
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 33)
+    ne = orc.density("lens", x, x, x, n_e0=5e25, LR=1e-3)
+    np.random.seed(3)
+    s0 = orc.init_beam(200, 4.5e-3, 20e-3, 5e-3, "z")
+    s0[:, 0] = [0, 0, -8e-3, 0, 0, orc.C_LIGHT]                       # starts in front of the cube
+    s0[:, 1] = [9e-3, 0, -5e-3, 0, 0, orc.C_LIGHT]                    # misses
+    s0[:, 2] = [4.9e-3, 0, -5e-3, 0.5 * orc.C_LIGHT, 0, np.sqrt(0.75) * orc.C_LIGHT]   # leaves through a side face
+    s0[:, 3] = [0, 1e-3, -5e-3, 0.8 * orc.C_LIGHT, 0, 0.6 * orc.C_LIGHT]               # steep: general integrator
+    res = {}
+    for rect in (False, True):
+        cube = pt.ElectronCube(x, x, x, dtype="float64", steps_per_cell=2, verbose=False)
+        cube.external_ne(ne)
+        old = pt.UNIFORM_RTOL
+        try:
+            pt.UNIFORM_RTOL = -1.0 if rect else old
+            cube.calc_dndr()
+        finally:
+            pt.UNIFORM_RTOL = old
+        assert (cube._nodes is not None) == rect
+        cube.s0 = s0
+        cube.extent = 5e-3
+        res[rect] = (np.asarray(cube.solve()), np.asarray(cube.sf), np.asarray(cube.status), cube.ray_steps)
+    (rf_u, sf_u, st_u, n_u), (rf_r, sf_r, st_r, n_r) = res[False], res[True]
+    np.testing.assert_array_equal(st_u, st_r)
+    assert st_r[1] & 8 and st_r[2] & 2 and st_r[3] & 16
+    np.testing.assert_allclose(rf_r, rf_u, rtol=0, atol=2e-11)           # same scheme, different rounding
+    np.testing.assert_allclose(sf_r[:3], sf_u[:3], rtol=0, atol=2e-11)
+    assert abs(n_r - n_u) <= 4                                            # general-integrator step counts may differ by one
+    cube = pt.ElectronCube(x, x, x, phaseshift=True, verbose=False)
+    cube.external_ne(ne)
+    old = pt.UNIFORM_RTOL
+    try:
+        pt.UNIFORM_RTOL = -1.0
+        cube.calc_dndr()
+    finally:
+        pt.UNIFORM_RTOL = old
+    cube.s0 = s0
+    with pytest.raises(NotImplementedError):
+        cube.solve()
 
 
 # ------------------------------------------------------------------------------------------- K3/K4

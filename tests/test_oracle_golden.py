@@ -177,3 +177,20 @@ def test_grf129_cube_and_first_batch(golden):
     field = orc.make_field(ne, x, x, x)
     rf, sf, _ = orc.solve(field, g["s0"][:, :32], float(g["extent"]), "z", rtol=1e-10, atol=1e-13, batch=32)
     np.testing.assert_allclose(rf, g["rf"][:, :32], rtol=1e-12, atol=1e-18)
+
+
+def test_rectilinear_axes_match_reference(golden):
+    """Non-uniformly spaced axes (numpy.gradient's non-uniform stencil, bisection in the interpolator)."""
+    g = golden("trace_rectilinear")
+    x, y, z = g["x"], g["y"], g["z"]
+    assert np.diff(x).max() / np.diff(x).min() > 3          # genuinely stretched
+    d = orc.calc_dndr(g["ne"], x, y, z)
+    sub = (slice(None, None, 2),) * 3
+    for k in ("dndx", "dndy", "dndz"):
+        np.testing.assert_array_equal(d[k][sub], g[k + "_sub"])
+    f = orc.GradientField(x, y, z, d["dndx"], d["dndy"], d["dndz"])
+    np.testing.assert_array_equal(f.dndr(g["pts"]), g["dndr_at_pts"])
+    for dr, n in (("z", 32), ("x", 16)):
+        rf, sf, _ = orc.solve(f, g["s0_" + dr][:, :n], float(g["extent_" + dr]), dr, rtol=1e-10, atol=1e-13, batch=32)
+        np.testing.assert_allclose(rf, g["rf_" + dr][:, :n], rtol=1e-12, atol=1e-18)
+        np.testing.assert_allclose(sf, g["sf_" + dr][:, :n], rtol=1e-13, atol=0)

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "tt_trace": (_i, [C.POINTER(TraceParams), _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
                           _vp, _vp]),
+    "tt_calc_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp]),
+    "tt_trace_axes": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tt_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _vp, _l, _vp, _vp]),
     "tt_optics_hist": (_i, [_vp, _l, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_optics_hist_perm": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "tt_optics_hist_weighted": (_i, [_vp, _l, _vp, _d, C.POINTER(Optic), _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

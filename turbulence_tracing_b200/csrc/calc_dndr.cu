@@ -25,7 +25,23 @@ struct DndrArgs {
     int third;         // the xyz axis that is neither z nor the u axis
     // FP32-in / FP32-out path: clip level in density units and -1/2 * (1/h | 1/2h) / nc per axis
     float clip_f, inv_nc_f, k1_f[3], k2_f[3];
+    // rectilinear grids (tt_calc_dndr_axes): node coordinates per xyz axis on the device, else null
+    const double* ax[3];
 };
+
+// numpy.gradient on a non-uniformly spaced axis (numpy/lib/_function_base_impl.py:1249-1334, edge_order=1):
+// interior  a f[i-1] + b f[i] + c f[i+1]  with  a = -dx2 / (dx1 (dx1 + dx2)),  b = (dx2 - dx1) / (dx1 dx2),
+// c = dx1 / (dx2 (dx1 + dx2));  faces  (f[1] - f[0]) / dx  and  (f[n-1] - f[n-2]) / dx, kept as differences
+// times 1/dx (stored in c resp. b).
+__device__ __forceinline__ void axis_coefficients(const double* __restrict__ x, int i, int n, double& a, double& b,
+                                                  double& c) {
+    if (i == 0) { a = 0.0; c = 1.0 / (x[1] - x[0]); b = -c; return; }
+    if (i == n - 1) { c = 0.0; b = 1.0 / (x[n - 1] - x[n - 2]); a = -b; return; }
+    const double dx1 = x[i] - x[i - 1], dx2 = x[i + 1] - x[i];
+    a = -dx2 / (dx1 * (dx1 + dx2));
+    b = (dx2 - dx1) / (dx1 * dx2);
+    c = dx1 / (dx2 * (dx1 + dx2));
+}
 
 // ne/nc clipped at ne_max.  Multiplying by 1/nc instead of dividing differs from the reference's
 // quotient by at most 1 ulp and keeps the kernel bandwidth-bound (an FP64 division costs ~30 instructions
@@ -49,6 +65,16 @@ __device__ __forceinline__ double axis_gradient(const TIn* __restrict__ ne, size
     return (ne_over_nc(ne, idx + stride, nc, ne_max) - ne_over_nc(ne, idx - stride, nc, ne_max)) * inv2h;
 }
 
+template <typename TIn>
+__device__ __forceinline__ double axis_gradient_nu(const TIn* __restrict__ ne, size_t idx, size_t stride, int i, int n,
+                                                   double a, double b, double c, double centre, double inv_nc,
+                                                   double ne_max) {
+    if (i == 0) return (ne_over_nc(ne, idx + stride, inv_nc, ne_max) - centre) * c;
+    if (i == n - 1) return (centre - ne_over_nc(ne, idx - stride, inv_nc, ne_max)) * b;
+    return __dadd_rn(__dadd_rn(__dmul_rn(a, ne_over_nc(ne, idx - stride, inv_nc, ne_max)), __dmul_rn(b, centre)),
+                     __dmul_rn(c, ne_over_nc(ne, idx + stride, inv_nc, ne_max)));
+}
+
 template <typename TIn, typename TOut, int PAR>
 __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ ne,
                                                         typename Vec4<TOut>::type* __restrict__ grid,
@@ -63,6 +89,21 @@ __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ 
     const int nx = a.n[0], ny = a.n[1], nz = a.n[2];
     const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
 
+    // rectilinear axes: the block's 32 z nodes, 32 u nodes and its one node of the third axis
+    const bool rect = a.ax[0] != nullptr;
+    __shared__ double coef[3][3][32];        // [0: z, 1: u, 2: third][a, b, c][node in tile]
+    if (rect) {
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        if (tid < 65) {
+            const int which = tid < 32 ? 0 : (tid < 64 ? 1 : 2);
+            const int axis = which == 0 ? 2 : (which == 1 ? ua : ta);
+            const int j = tid & 31;
+            const int i = which == 0 ? z0 + j : (which == 1 ? u0 + j : t);
+            if (i < a.n[axis]) axis_coefficients(a.ax[axis], i, a.n[axis], coef[which][0][j], coef[which][1][j], coef[which][2][j]);
+        }
+        __syncthreads();
+    }
+
     // phase 1: compute, coalesced along z
     const int iz = z0 + threadIdx.x;
 #pragma unroll
@@ -73,7 +114,19 @@ __global__ void __launch_bounds__(256) calc_dndr_kernel(const TIn* __restrict__ 
             i3[2] = iz; i3[ua] = iu; i3[ta] = t;
             const size_t idx = (size_t)i3[0] * sx + (size_t)i3[1] * sy + i3[2];
             V4 o;
-            if constexpr (sizeof(TIn) == 4 && sizeof(TOut) == 4) {
+            if (rect) {
+                const double c = ne_over_nc(ne, idx, a.inv_nc, a.ne_max);
+                const size_t st[3] = {sx, sy, 1};
+                double g[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int which = ax == 2 ? 0 : (ax == ua ? 1 : 2);
+                    const int j = which == 0 ? (int)threadIdx.x : (which == 1 ? r + (int)threadIdx.y : 0);
+                    g[ax] = -0.5 * axis_gradient_nu(ne, idx, st[ax], i3[ax], a.n[ax], coef[which][0][j], coef[which][1][j],
+                                                    coef[which][2][j], c, a.inv_nc, a.ne_max);
+                }
+                o.x = (TOut)g[F0]; o.y = (TOut)g[F1]; o.z = (TOut)g[F2]; o.w = (TOut)c;
+            } else if constexpr (sizeof(TIn) == 4 && sizeof(TOut) == 4) {
                 // FP32 cube in, FP32 grid out: the difference of two neighbouring FP32 densities is exact in
                 // FP32 (Sterbenz), so nothing is gained by FP64 here and the conversions would make the
                 // kernel XU-bound; differences first, one multiplication by -1/2 / (h nc) afterwards
@@ -132,9 +185,9 @@ static int launch_dndr(const void* ne, void* grid, const DndrArgs& a, cudaStream
 
 }  // namespace tt
 
-extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3],
-                            const double spacing_xyz[3], int par, double nc, double ne_max,
-                            void* grid4_dev, int grid_dtype, tt_stream_t stream) {
+static int calc_dndr_impl(const void* ne_dev, int ne_dtype, const int n_xyz[3], const double spacing_xyz[3],
+                          const double* const axes_dev[3], int par, double nc, double ne_max, void* grid4_dev,
+                          int grid_dtype, tt_stream_t stream) {
     using namespace tt;
     TT_REQUIRE(ne_dev && grid4_dev && n_xyz && spacing_xyz, "tt_calc_dndr: null pointer");
     TT_REQUIRE(par >= 0 && par <= 2, "tt_calc_dndr: par must be 0, 1 or 2 (got %d)", par);
@@ -153,6 +206,7 @@ extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3]
     Frame f = frame_of(par);
     for (int i = 0; i < 3; ++i) a.fa[i] = f.a[i];
     a.third = 3 - 2 - a.fa[0];   // axes are {0,1,2}; z = 2 and u = fa[0] are taken
+    for (int i = 0; i < 3; ++i) a.ax[i] = axes_dev ? axes_dev[i] : nullptr;
     a.nc = nc;
     a.inv_nc = 1.0 / nc;
     a.ne_max = ne_max;
@@ -168,4 +222,19 @@ extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3]
     if (ne_dtype == TT_F64 && grid_dtype == TT_F32) return launch_dndr<double, float>(ne_dev, grid4_dev, a, s);
     if (ne_dtype == TT_F32 && grid_dtype == TT_F64) return launch_dndr<float, double>(ne_dev, grid4_dev, a, s);
     return launch_dndr<double, double>(ne_dev, grid4_dev, a, s);
+}
+
+extern "C" int tt_calc_dndr(const void* ne_dev, int ne_dtype, const int n_xyz[3],
+                            const double spacing_xyz[3], int par, double nc, double ne_max,
+                            void* grid4_dev, int grid_dtype, tt_stream_t stream) {
+    return calc_dndr_impl(ne_dev, ne_dtype, n_xyz, spacing_xyz, nullptr, par, nc, ne_max, grid4_dev, grid_dtype, stream);
+}
+
+extern "C" int tt_calc_dndr_axes(const void* ne_dev, int ne_dtype, const int n_xyz[3], const double* x_dev,
+                                 const double* y_dev, const double* z_dev, int par, double nc, double ne_max,
+                                 void* grid4_dev, int grid_dtype, tt_stream_t stream) {
+    TT_REQUIRE(x_dev && y_dev && z_dev, "tt_calc_dndr_axes: null axis pointer");
+    const double* const axes[3] = {x_dev, y_dev, z_dev};
+    const double unit[3] = {1.0, 1.0, 1.0};      // unused by the rectilinear branch
+    return calc_dndr_impl(ne_dev, ne_dtype, n_xyz, unit, axes, par, nc, ne_max, grid4_dev, grid_dtype, stream);
 }

@@ -34,19 +34,26 @@ _AXIS = {"x": 0, "y": 1, "z": 2}
 UNIFORM_RTOL = 1e-9
 
 
-def _uniform_spacing(a, name):
+def _axis_spacing(a, name):
+    """(origin, mean spacing, uniform?) of a coordinate axis.  Axes whose node spacing deviates from
+    the mean by more than UNIFORM_RTOL of the axis length are rectilinear: they take the
+    ``tt_*_axes`` kernels (node coordinates on the device) instead of origin + spacing."""
     a = np.asarray(a, dtype=np.float64)
     if a.ndim != 1 or a.size < 2:
         raise ValueError(f"axis {name} must be a 1-D array with at least 2 points")
     h = (a[-1] - a[0]) / (a.size - 1)
-    if not h > 0:
-        raise ValueError(f"axis {name} must be ascending")
-    dev = np.max(np.abs(np.diff(a) - h))
-    if dev > UNIFORM_RTOL * abs(a[-1] - a[0]):
-        raise NotImplementedError(
-            f"axis {name} is not uniformly spaced (max deviation {dev:.3e} m); the CUDA path "
-            "supports uniform axes only and there is no CPU fallback")
-    return float(a[0]), float(h)
+    d = np.diff(a)
+    if not h > 0 or not np.all(d > 0):
+        raise ValueError(f"axis {name} must be strictly ascending")
+    uniform = bool(np.max(np.abs(d - h)) <= UNIFORM_RTOL * abs(a[-1] - a[0]))
+    return float(a[0]), float(h), uniform
+
+
+def _uniform_spacing(a, name):
+    o, h, uniform = _axis_spacing(a, name)
+    if not uniform:
+        raise NotImplementedError(f"axis {name} is not uniformly spaced; this entry point needs uniform axes")
+    return o, h
 
 
 class _GradInterp:
@@ -101,6 +108,7 @@ class ElectronCube:
         self.verbose = bool(verbose)
         self._ne = None          # host array or device tensor as supplied
         self._grid = None        # device tensor [nw, nv, nu, 4]
+        self._nodes = None       # device node coordinates (x, y, z) when the axes are not uniformly spaced
         self._s0 = None
         self.ray_steps = 0       # RK4 steps taken inside the cube by the last solve()
         self.last_solve_seconds = None
@@ -116,10 +124,9 @@ class ElectronCube:
         return (len(self.x), len(self.y), len(self.z))
 
     def _geometry(self):
-        ox, hx = _uniform_spacing(self.x, "x")
-        oy, hy = _uniform_spacing(self.y, "y")
-        oz, hz = _uniform_spacing(self.z, "z")
-        return (ox, oy, oz), (hx, hy, hz)
+        """(origin, mean spacing, rectilinear?) per xyz axis."""
+        info = [_axis_spacing(a, n) for a, n in ((self.x, "x"), (self.y, "y"), (self.z, "z"))]
+        return tuple(i[0] for i in info), tuple(i[1] for i in info), not all(i[2] for i in info)
 
     @property
     def _par(self):
@@ -269,7 +276,7 @@ class ElectronCube:
         self.ne_max = ne_max
         self.VerdetConst = VERDET * lwl**2          # rad / (T m^2)
         self._aux = None
-        origin, spacing = self._geometry()
+        origin, spacing, rect = self._geometry()
         ne = self._ne
         if tuple(ne.shape) != self.shape:
             raise ValueError(f"ne has shape {tuple(ne.shape)}, expected {self.shape}")
@@ -287,9 +294,18 @@ class ElectronCube:
         if grid is None or tuple(grid.shape) != gshape or grid.dtype != gdt:
             self._grid = grid = None          # release the old grid before allocating (2-17 GB)
             grid = torch.empty(gshape, dtype=gdt, device="cuda")
-        _lib.check(lib.tt_calc_dndr(_lib.ptr(ne_dev), _lib.dtype_code(ne_dev.dtype), _lib.i3(n), _lib.d3(spacing),
-                                    par, float(self.nc), float(ne_max), _lib.ptr(grid),
-                                    _lib.dtype_code(gdt), _lib.stream_ptr()), "tt_calc_dndr")
+        self._nodes = None
+        if rect:      # non-uniformly spaced axes: node coordinates go to the device (include/tt_b200.h, tt_*_axes)
+            self._nodes = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
+                           for a in (self.x, self.y, self.z)]
+            _lib.check(lib.tt_calc_dndr_axes(_lib.ptr(ne_dev), _lib.dtype_code(ne_dev.dtype), _lib.i3(n),
+                                             *(_lib.ptr(a) for a in self._nodes), par, float(self.nc), float(ne_max),
+                                             _lib.ptr(grid), _lib.dtype_code(gdt), _lib.stream_ptr()),
+                       "tt_calc_dndr_axes")
+        else:
+            _lib.check(lib.tt_calc_dndr(_lib.ptr(ne_dev), _lib.dtype_code(ne_dev.dtype), _lib.i3(n), _lib.d3(spacing),
+                                        par, float(self.nc), float(ne_max), _lib.ptr(grid),
+                                        _lib.dtype_code(gdt), _lib.stream_ptr()), "tt_calc_dndr")
         self._grid, self._frame, self._origin, self._spacing = grid, fa, origin, spacing
         self.dndx_interp, self.dndy_interp, self.dndz_interp = (_GradInterp(self, k) for k in range(3))
 
@@ -321,6 +337,11 @@ class ElectronCube:
         if xd.dim() != 2 or xd.shape[0] != 3:
             raise ValueError("x must have shape (3, N)")
         out = torch.empty_like(xd)
+        if self._nodes is not None:
+            _lib.check(lib.tt_dndr_axes(_lib.ptr(g), _lib.dtype_code(g.dtype), _lib.i3(self.shape),
+                                        *(_lib.ptr(a) for a in self._nodes), self._par, _lib.ptr(xd), xd.shape[1],
+                                        _lib.ptr(out), _lib.stream_ptr()), "tt_dndr_axes")
+            return out.cpu().numpy() if host else DeviceArray(out)
         _lib.check(lib.tt_dndr(_lib.ptr(g), _lib.dtype_code(g.dtype), _lib.i3(self.shape), _lib.d3(self._origin),
                                _lib.d3(self._spacing), self._par, _lib.ptr(xd), xd.shape[1], _lib.ptr(out),
                                _lib.stream_ptr()), "tt_dndr")
@@ -390,6 +411,10 @@ class ElectronCube:
             raise ValueError("s0 must have shape (6, Np) (or (9, Np) with amplitude, phase, polarisation rows)")
         Np = shape0[1]
         use_aux = self.B_on or self.inv_brems or self.phaseshift
+        nodes = self._nodes
+        if nodes is not None and use_aux:
+            raise NotImplementedError("B_on / inv_brems / phaseshift need uniformly spaced axes "
+                                      "(the rectilinear-grid kernel integrates the trajectory only)")
         if Np == 0:                                   # empty bundle: nothing to launch
             self.rf = DeviceArray(torch.empty((4, 0), dtype=torch.float64, device="cuda"))
             self.sf = DeviceArray(torch.empty((6, 0), dtype=torch.float64, device="cuda")) if self.keep_sf else None
@@ -430,7 +455,11 @@ class ElectronCube:
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            if use_aux:
+            if nodes is not None:
+                _lib.check(lib.tt_trace_axes(C.byref(p), *(_lib.ptr(a) for a in nodes), _lib.ptr(grid), _lib.ptr(s0b), n,
+                                             _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(steps),
+                                             _lib.ptr(status), stream), "tt_trace_axes")
+            elif use_aux:
                 _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0b), n,
                                             _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out),
                                             _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace_aux")
