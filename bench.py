@@ -367,20 +367,33 @@ def run_gpu_arm(args, wl):
         cube2 = make_cube()
         ne_np, s0_np = ne_host.numpy(), s0_host.numpy()
 
+        e2e_events = []
+
         def step_e2e():
+            marks = []
+            mark(marks)
             cube2.external_ne(ne_np)                # host numpy -> H2D inside calc_dndr
             cube2.calc_dndr(LWL)
+            mark(marks)
             cube2.s0 = s0_np                        # host numpy -> H2D inside solve
             rf = cube2.solve()
+            mark(marks)
             sh = rtm.Shadowgraphy(rf)
             sh.solve()
             sh.histogram()                          # D2H of the histogram inside
             H = ttd.allreduce_histograms([sh.H_dev])[0]
             _ = cube2.ray_steps                     # D2H of the counter
+            mark(marks)
+            e2e_events.append(marks)
             return H, cube2._steps_dev
 
         ms2, tot2, _, _ = timed(step_e2e, cube2, 2, args.steps)
+        e2e_names = ["h2d_cube+calc_dndr", "h2d_rays+sort+trace", "optics+hist+d2h"]
         e2e = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / args.steps,
+               "phases_ms": {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in e2e_events[-args.steps:]]))
+                             for i, n in enumerate(e2e_names)},
+               "trace_launches_per_step": len(trace_ms) // max(args.steps, 1),
+               "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(args.steps, 1),
                "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
                "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),
                "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}

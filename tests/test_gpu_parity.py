@@ -204,14 +204,15 @@ def test_rectilinear_edge_cases_and_uniform_equivalence(tt):
         finally:
             pt.UNIFORM_RTOL = old
         assert (cube._nodes is not None) == rect
+        cube.kernel_variant = 1             # uniform side: the gather kernel (same plane-marching scheme)
         cube.s0 = s0
         cube.extent = 5e-3
         res[rect] = (np.asarray(cube.solve()), np.asarray(cube.sf), np.asarray(cube.status), cube.ray_steps)
     (rf_u, sf_u, st_u, n_u), (rf_r, sf_r, st_r, n_r) = res[False], res[True]
     np.testing.assert_array_equal(st_u, st_r)
     assert st_r[1] & 8 and st_r[2] & 2 and st_r[3] & 16
-    np.testing.assert_allclose(rf_r, rf_u, rtol=0, atol=2e-11)           # same scheme, different rounding
-    np.testing.assert_allclose(sf_r[:3], sf_u[:3], rtol=0, atol=2e-11)
+    np.testing.assert_allclose(rf_r, rf_u, rtol=0, atol=1e-10)           # same scheme, different rounding
+    np.testing.assert_allclose(sf_r[:3], sf_u[:3], rtol=0, atol=1e-10)
     assert abs(n_r - n_u) <= 4                                            # general-integrator step counts may differ by one
     cube = pt.ElectronCube(x, x, x, phaseshift=True, verbose=False)
     cube.external_ne(ne)

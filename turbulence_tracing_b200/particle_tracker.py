@@ -491,8 +491,15 @@ class ElectronCube:
             bufs = [torch.empty((6, chunk), dtype=torch.float64, device="cuda") for _ in range(2)]
             free = [None, None]                            # compute-done events per buffer
             copy.wait_stream(main)
-            for ci, lo in enumerate(range(0, Np, chunk)):
-                n = min(chunk, Np - lo)
+            # the first chunks are short (chunk/8, /4, /2) so that tracing starts ~1.5 ms after the first byte
+            # instead of after a whole chunk's upload (12 ms at PCIe 5 rates)
+            bounds, lo, n = [], 0, max(chunk // 8, 1)
+            while lo < Np:
+                n = min(n, Np - lo)
+                bounds.append((lo, n))
+                lo += n
+                n = min(2 * n, chunk)
+            for ci, (lo, n) in enumerate(bounds):
                 b = ci % 2
                 with torch.cuda.stream(copy):
                     if free[b] is not None:
