@@ -19,6 +19,8 @@ traces RAYS rays), the ne cube is broadcast from rank 0 once.
   cpu_baseline : the reference's scipy path (oracle port: solve_ivp RK45 at default tolerances over
           RegularGridInterpolator, multiprocessing.Pool over ray bundles as example_multiprocess.py)
           on a bounded sample of the same cube, on this box's host cores
+  cpu_baseline_c : the same sample through the plain-C restatement of that path (oracle/tt_oracle.c,
+          one thread per bundle) -- the stronger CPU baseline, reported next to the scipy one
 
 --impl reference times that CPU path alone (rank 0 only).
 """
@@ -187,6 +189,34 @@ def cpu_reference_step(rays_per_worker, cores, min_seconds=10.0, max_rounds=6):
     return tot
 
 
+def cpu_c_port_sample(cores, rays_per_bundle, min_seconds=3.0, max_rounds=40):
+    """The same workload through the plain-C restatement of the reference path (oracle/tt_oracle.c: numpy.gradient,
+    RegularGridInterpolator and solve_ivp RK45 written out, scipy's default tolerances, one adaptive step sequence
+    per bundle like ElectronCube.solve), bundles handed to `cores` threads.  Reported next to the scipy figure as
+    the stronger CPU baseline; the gradient arrays are shared with the scipy field (no copy)."""
+    from oracle import c_oracle as orc_c
+    from oracle import ref_numpy as orc
+    f = _CPU["field"]
+    x, y, z = f.ix.grid
+    cf = orc_c.GradientField(x, y, z, f.ix.values, f.iy.values, f.iz.values)
+    tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0, "rounds": 0}
+    while tot["rounds"] < max_rounds and tot["seconds"] < min_seconds:
+        n = cores * 4 * rays_per_bundle
+        np.random.seed(5000 + tot["rounds"])
+        s0 = orc.init_beam(n, BEAM_SIZE, DIVERGENCE, EXTENT, "z")
+        t0 = time.perf_counter()
+        rf, _, evals = orc_c.solve(cf, s0, EXTENT, "z", batch=rays_per_bundle, threads=cores)
+        H, _, _ = orc.histogram(orc.detector("shadowgraphy", rf))
+        tot["seconds"] += time.perf_counter() - t0
+        tot["rays"] += n
+        tot["ray_rhs_evals"] += evals
+        tot["rounds"] += 1
+    return {"value": tot["ray_rhs_evals"] / 4.0 / tot["seconds"], "unit": "ray-steps/s", "cores": cores, "kind": "port",
+            "rays_per_s": tot["rays"] / tot["seconds"],
+            "sample": f"C restatement (oracle/tt_oracle.c), {cores} threads x {4 * tot['rounds']} bundles of {rays_per_bundle} rays, "
+                      f"RK45 default rtol=1e-3, ray-steps = nfev*rays/4; {tot['seconds']:.1f} s"}
+
+
 def cpu_line_fields(res, cores, rays_per_worker, M, kind="port"):
     steps = res["ray_rhs_evals"] / 4.0           # 4 RHS evaluations = 1 RK4-equivalent ray-step
     return {"value": steps / res["seconds"], "unit": "ray-steps/s", "cores": cores, "kind": kind,
@@ -219,13 +249,17 @@ def run_reference_arm(args, wl):
         for k in tot:
             tot[k] += r[k]
     cb = cpu_line_fields(tot, cores, rays_per_worker, M)
+    try:
+        cb_c = cpu_c_port_sample(cores, rays_per_worker)
+    except Exception as e:                  # reported, never silently dropped
+        cb_c = {"value": None, "unit": "ray-steps/s", "cores": cores, "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
     line = {"metric": "ray-steps/s", "value": cb["value"], "unit": "ray-steps/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "rays_per_s": cb["rays_per_s"],
             "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": tot["rays"] // max(args.steps, 1)},
-            "cpu_baseline": cb,
+            "cpu_baseline": cb, "cpu_baseline_c": cb_c,
             "e2e": {"value": cb["value"], "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -415,8 +449,20 @@ def run_gpu_arm(args, wl):
                         "and shared by neighbouring rays through L1/L2, so DRAM traffic is <1% of the algorithmic "
                         "bytes (mostly the permuted s0 gather / rf scatter) and frac > 1 -- see profiles/"}
 
+    # secondary bound: the FP32 pipe (what actually limits the register-resident kernel).  Static issue-cycle count
+    # per warp-step from the committed opcode mix x the live ray-step rate, against 4 FMA-pipe issue slots per SM
+    # and clock (148 SMs) at the SM clock sampled during the timed region.
+    ncu_e = roofline["ncu"] or {}
+    if ncu_e.get("fma_pipe_slots_per_warp_step") and clocks and clocks.get("sm_mhz"):
+        slots = ncu_e["fma_pipe_slots_per_warp_step"]
+        ach = steps_per_launch / 32.0 * slots / (kernel_ms * 1e-3)
+        pk = 148 * 4 * clocks["sm_mhz"] * 1e6
+        roofline["fp32_pipe"] = {"bound": "fp32 pipe issue", "achieved": ach, "peak": pk, "unit": "warp-instruction slots/s",
+                                 "frac": ach / pk, "slots_per_warp_step": slots,
+                                 "note": "peak = 148 SMs x 4 sub-partitions x sampled SM clock; slots from profiles/traffic.json"}
+
     # ---- CPU baseline on a bounded sample of the same cube (rank 0, N = 1 only) ----------------------
-    cpu = None
+    cpu = cpu_c = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             # a fresh process (no CUDA context to fork) runs the CPU path on the very same cube
@@ -426,7 +472,8 @@ def run_gpu_arm(args, wl):
                                   "--cube-file", path, "--steps", "1", "--warmup", "0", "--cpu-rays",
                                   str(args.cpu_rays)], capture_output=True, text=True, timeout=1500)
             os.remove(path)
-            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu, cpu_c = ref_line["cpu_baseline"], ref_line.get("cpu_baseline_c")
         except Exception as e:      # reported, never silently dropped
             cpu = {"value": None, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {type(e).__name__}: {e}"}
@@ -446,7 +493,7 @@ def run_gpu_arm(args, wl):
             "e2e": e2e, "gpu_launches": 5 * args.steps * world,
             "gpu_launches_note": "per step and GPU: calc_dndr_kernel, morton_key_kernel, trace_event_kernel_f32x2, trace_kernel "
                                  "(second pass over deferred rays), optics_hist_kernel (+ 6 CUB radix-sort kernels)",
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "phases_ms": phases,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "clocks": clocks, "phases_ms": phases,
             "histogram_sum": int(H_dev.sum().item()),
         }
         emit(line)

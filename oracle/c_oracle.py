@@ -51,7 +51,8 @@ def load():
         lib.tto_solve_ivp_rk45.argtypes = [fp, dp, C.c_long, C.c_double, C.c_double, C.c_double, dp,
                                            C.POINTER(C.c_long), C.POINTER(C.c_long), dp, C.c_long]
         lib.tto_solve_ivp_rk45.restype = C.c_long
-        lib.tto_solve.argtypes = [fp, dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, dp, C.c_int]
+        lib.tto_solve.argtypes = [fp, dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, dp, C.c_int,
+                                  C.POINTER(C.c_long)]
         lib.tto_solve.restype = C.c_longlong
         lib.tto_ray_at_exit.argtypes = [dp, C.c_long, C.c_double, C.c_int, dp]
         lib.tto_ray_at_exit.restype = None
@@ -112,22 +113,26 @@ def ray_at_exit(sf, extent, probing_direction="z"):
     return rf
 
 
-def solve(field, s0, extent, probing_direction="z", rtol=1e-3, atol=1e-6, batch=None, threads=0):
+def solve(field, s0, extent, probing_direction="z", rtol=1e-3, atol=1e-6, batch=None, threads=0, strict=True):
     """Same contract as ``oracle.ref_numpy.solve``: (rf, sf, ray_rhs_evals).
 
     ``batch=None`` is the reference's ``ElectronCube.solve`` (one adaptive step sequence for the whole
     bundle, particle_tracker.py:317-330); ``batch=k`` integrates bundles of k rays independently
     (``threads`` POSIX threads, 0 = all cores), ``batch=1`` gives every ray its own step control.
+    A bundle whose step size underflows (solve_ivp's status -1) raises, or with ``strict=False`` comes back NaN.
     """
     lib = load()
     s0 = _f64(s0)
     n = s0.shape[1]
     sf = np.empty_like(s0)
     T = np.sqrt(8.0) * float(extent) / C_LIGHT
+    failed = C.c_long()
     evals = lib.tto_solve(C.byref(field.c), _p(s0), n, int(batch or n), T, float(rtol), float(atol), _p(sf),
-                          int(threads))
+                          int(threads), C.byref(failed))
     if evals < 0:
-        raise RuntimeError(f"tto_solve failed ({evals}): " + ("out of memory" if evals == -1 else "step size underflow"))
+        raise MemoryError("tto_solve: out of memory")
+    if failed.value and strict:
+        raise RuntimeError(f"tto_solve: step size underflow in {failed.value} bundle(s)")
     return ray_at_exit(sf, extent, probing_direction), sf, int(evals)
 
 

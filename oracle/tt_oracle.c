@@ -311,7 +311,9 @@ long tto_solve_ivp_rk45(const tto_field* F, const double* y0, long n, double T, 
 /* Many bundles of `batch` rays each (the last one may be shorter), one solve_ivp call per bundle like the
  * reference run under multiprocessing.Pool (example_multiprocess.py:41-51); bundles are handed out to
  * `threads` POSIX threads (this image's gcc has no libgomp).  s0, sf: (6, n) row-major.  Returns the sum
- * over bundles of nfev * rays (ray-RHS evaluations), negative on failure. */
+ * over bundles of nfev * rays (ray-RHS evaluations), negative on allocation failure.  A bundle whose step
+ * size underflows (solve_ivp status -1, e.g. a ray that slides along a face of the cube, where the field
+ * jumps to zero) gets NaN outputs and is counted in *n_failed. */
 typedef struct {
     const tto_field* F;
     const double* s0;
@@ -320,7 +322,8 @@ typedef struct {
     double T, rtol, atol;
     long next;                 /* next bundle to hand out (guarded by mu) */
     long long total;
-    int bad;
+    int bad;                   /* 1: allocation failure */
+    long n_failed;             /* bundles whose step size underflowed (solve_ivp status -1): outputs set to NaN */
     pthread_mutex_t mu;
 } solve_job;
 
@@ -340,10 +343,14 @@ static void* solve_worker(void* arg) {
             nfev = tto_solve_ivp_rk45(J->F, in, m, J->T, J->rtol, J->atol, out, NULL, NULL, NULL, 0);
             if (nfev >= 0)
                 for (int k = 0; k < 6; ++k) memcpy(J->sf + (size_t)k * n + lo, out + k * m, sizeof(double) * (size_t)m);
+            else if (nfev == -2)
+                for (int k = 0; k < 6; ++k)
+                    for (long r = 0; r < m; ++r) J->sf[(size_t)k * n + lo + r] = NAN;
             free(in);
         }
         pthread_mutex_lock(&J->mu);
-        if (nfev < 0) J->bad |= (nfev == -1 ? 1 : 2);
+        if (nfev == -1) J->bad |= 1;
+        else if (nfev == -2) J->n_failed += 1;
         else J->total += (long long)nfev * m;
         pthread_mutex_unlock(&J->mu);
     }
@@ -356,12 +363,13 @@ int tto_max_threads(void) {
 }
 
 long long tto_solve(const tto_field* F, const double* s0, long n, long batch, double T, double rtol, double atol,
-                    double* sf, int threads) {
+                    double* sf, int threads, long* n_failed) {
+    if (n_failed) *n_failed = 0;
     if (n <= 0) return 0;
     if (batch <= 0 || batch > n) batch = n;
     solve_job J;
     J.F = F; J.s0 = s0; J.sf = sf; J.n = n; J.batch = batch; J.nb = (n + batch - 1) / batch;
-    J.T = T; J.rtol = rtol; J.atol = atol; J.next = 0; J.total = 0; J.bad = 0;
+    J.T = T; J.rtol = rtol; J.atol = atol; J.next = 0; J.total = 0; J.bad = 0; J.n_failed = 0;
     pthread_mutex_init(&J.mu, NULL);
     if (threads <= 0) threads = tto_max_threads();
     if (threads > J.nb) threads = (int)J.nb;
@@ -377,6 +385,7 @@ long long tto_solve(const tto_field* F, const double* s0, long n, long batch, do
         free(th);
     }
     pthread_mutex_destroy(&J.mu);
+    if (n_failed) *n_failed = J.n_failed;
     return J.bad ? -(long long)J.bad : J.total;
 }
 

@@ -114,3 +114,114 @@ def test_non_cubic_cells_probing_y_against_c_oracle(tt):
     p, a, _ = _errors(rf32_2, ref)
     print(f"fp32 2 steps/cell vs C oracle: {p:.2e} m = {p / PIXEL_M:.1e} pixel, angle {a:.1e} of rms")
     assert p <= 1e-2 * PIXEL_M                            # coarse cells (156 um = 8x the 513^3 cell): truncation
+
+
+def _stretched_case():
+    """the edge-case bundle of tests/test_host_kernels.py (verified there on the CPU from the kernel's source)"""
+    C_LIGHT = orc.C_LIGHT
+    rng = np.random.RandomState(3)
+    x = np.cumsum(np.r_[0, np.geomspace(0.05e-3, 0.6e-3, 24)]) - 2e-3           # cell sizes 50 .. 600 um
+    y = np.sort(np.r_[-3e-3, 3e-3, rng.uniform(-3e-3, 3e-3, 20)])
+    z = np.linspace(-2e-3, 4e-3, 31) + 0.08e-3 * np.sin(np.linspace(0, 9, 31))
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    ne = 3e25 * (1 + 0.5 * np.sin(1500 * X) * np.cos(1100 * Y) + 0.3 * np.sin(900 * Z + 2000 * X * Y * 1e3))
+    n = 64
+    s0 = np.zeros((6, n))
+    s0[0] = rng.uniform(x[0] + 0.5e-3, x[-1] - 0.5e-3, n)
+    s0[1] = rng.uniform(-2e-3, 2e-3, n)
+    s0[2] = -5e-3
+    chi, phi = 2e-3 * rng.randn(n), np.pi * rng.rand(n)
+    s0[3], s0[4], s0[5] = C_LIGHT * np.sin(chi) * np.cos(phi), C_LIGHT * np.sin(chi) * np.sin(phi), C_LIGHT * np.cos(chi)
+    s0[0, 0], s0[1, 0] = x[5], y[7]
+    s0[0, 1], s0[1, 1], s0[3, 1] = x[-1], 0.0, 0.0
+    s0[2, 2] = z[4]
+    s0[2, 3] = 0.5 * (z[10] + z[11])
+    s0[2, 4] = z[-1]
+    s0[0, 5], s0[3, 5], s0[5, 5] = x[-1] - 1e-5, 0.2 * C_LIGHT, np.sqrt(1 - 0.04) * C_LIGHT      # side exit
+    s0[5, 6] = -C_LIGHT                                                                           # backward
+    s0[3, 7], s0[5, 7] = 0.8 * C_LIGHT, 0.6 * C_LIGHT                                            # steep
+    s0[0, 8] = x[-1] + 1e-3                                                                       # misses
+    return x, y, z, ne, s0, [1, 5, 6, 7, 8]
+
+
+def test_rectilinear_event_marching_and_second_pass(tt):
+    """tt_trace_axes variant 0 (event marching + gather second pass) against variant 2 (gather alone) and the C
+    oracle on strongly stretched, asymmetric axes with rays in front of the cube, on nodes / faces, leaving
+    through a side face, backward, steep, missing."""
+    x, y, z, ne, s0, special = _stretched_case()
+    out = {}
+    for variant in (0, 2):
+        cube = tt.particle_tracker.ElectronCube(x, y, z, dtype="float64", steps_per_cell=8, verbose=False)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        assert cube._nodes is not None
+        cube.kernel_variant = variant
+        cube.s0 = s0
+        cube.extent = 5e-3
+        rf = np.asarray(cube.solve())
+        out[variant] = (rf, np.asarray(cube.sf), np.asarray(cube.status), cube.ray_steps)
+    (rf0, sf0, st0, n0), (rf2, sf2, st2, n2) = out[0], out[2]
+    np.testing.assert_array_equal(rf0[:, special[1:]], rf2[:, special[1:]])     # the second pass IS the gather kernel
+    np.testing.assert_array_equal(st0[special[1:]], st2[special[1:]])
+    assert st0[8] & 8 and st0[5] & 2 and st0[7] & 16 and not np.any(st0 == 0xFF)
+    marched = np.ones(s0.shape[1], bool)
+    marched[special] = False
+    assert np.all(st0[marched] == 1) and np.all(st2[marched] & 1)
+    field = orc_c.make_field(ne, x, y, z)
+    ref, sf_ref, _ = orc_c.solve(field, s0, 5e-3, "z", rtol=1e-13, atol=1e-16, batch=1, strict=False)
+    p0, a0, _ = _errors(rf0[:, marched], ref[:, marched])
+    p2, a2, _ = _errors(rf2[:, marched], ref[:, marched])
+    print(f"stretched axes, 8 steps/cell vs C oracle: event marching {p0:.1e} m / {a0:.1e} of rms; gather {p2:.1e} m / {a2:.1e}")
+    assert p0 <= 1e-9 and a0 <= 1e-6
+    assert p2 <= 1e-5 * BEAM and a2 <= 1e-4
+    np.testing.assert_allclose(sf0[:3, marched], sf_ref[:3, marched], rtol=0, atol=1e-8)
+    assert abs(n0 - n2) <= 8 * 2                       # same plane arrivals (the general integrator may differ by a step)
+
+
+def test_rectilinear_event_marching_beam_against_c_oracle(tt):
+    """a full beam through a stretched 97 x 81 x 129 mesh: FP64 criterion at 2 steps/cell, float32 grid within the
+    pixel bar, and the speed of the two rectilinear kernels"""
+    import torch
+    t = np.linspace(-1, 1, 97)
+    x = 5e-3 * np.tanh(1.6 * t) / np.tanh(1.6)                       # fine in the middle, coarse outside
+    y = np.linspace(-5e-3, 5e-3, 81)
+    z = -5e-3 + 1e-2 * np.linspace(0, 1, 129) ** 1.5                # fine at the entry face
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    rng = np.random.RandomState(8)
+    f = np.zeros_like(X)
+    for _ in range(24):
+        k = rng.randn(3)
+        k *= 2 * np.pi / (rng.uniform(1.2e-3, 5e-3) * np.linalg.norm(k))
+        f += rng.randn() * np.cos(k[0] * X + k[1] * Y + k[2] * Z + rng.uniform(0, 2 * np.pi))
+    ne = 1e25 * np.clip(1 + 0.3 * f / f.std(), 0, None)
+    np.random.seed(13)
+    s0 = orc.init_beam(200_000, BEAM, 0.05e-3, 5e-3, "z")
+    nref = 4096
+    ref = orc_c.solve(orc_c.make_field(ne, x, y, z), s0[:, :nref], 5e-3, "z", rtol=1e-13, atol=1e-16, batch=1)[0]
+    ms = {}
+    for dtype, variant, spc in (("float64", 0, 2), ("float64", 2, 2), ("float32", 0, 2)):
+        cube = tt.particle_tracker.ElectronCube(x, y, z, dtype=dtype, steps_per_cell=spc, verbose=False)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        cube.kernel_variant = variant
+        cube.s0 = s0
+        cube.extent = 5e-3
+        cube.solve()                                                  # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rf = cube.solve()
+        e1.record()
+        torch.cuda.synchronize()
+        ms[(dtype, variant)] = e0.elapsed_time(e1)
+        assert int((cube.status.torch == 1).sum()) == s0.shape[1]
+        assert cube.ray_steps == spc * 128 * s0.shape[1]
+        p, a, rms = _errors(np.asarray(rf)[:, :nref], ref)
+        print(f"stretched 97x81x129, {dtype} grid, variant {variant}, {spc} steps/cell: {p:.2e} m, {a:.1e} of rms "
+              f"({rms * 1e3:.2f} mrad); sort + trace of 2e5 rays {ms[(dtype, variant)]:.2f} ms")
+        if dtype == "float64" and variant == 0:
+            assert p <= 1e-5 * BEAM and a <= 1e-5
+        elif dtype == "float64":                     # gather: 2nd order where a stage straddles a u / v cell face
+            assert p <= 1e-4 * BEAM and a <= 1e-3
+        else:
+            assert p <= 1e-3 * PIXEL_M
+    print(f"event marching vs gather on the rectilinear grid: {ms[('float64', 2)] / ms[('float64', 0)]:.1f}x")

@@ -11,18 +11,9 @@
 //     the ray's previous cell (rays move a fraction of a cell per step; the first look-up is a bisection).
 // This is the general-geometry path, not the speed path: all arithmetic is FP64, the grid is read as
 // float4 or double4.
-#include "trace_common.cuh"
+#include "trace_axes_event.cuh"     // AxesArgs, find_cell, axes_event_ray (+ trace_common.cuh)
 
 namespace tt {
-
-struct AxesArgs {
-    int n[3];                 // nu, nv, nw
-    const double* ax[3];      // node coordinates per frame axis (device)
-    int fa[3];                // frame axis -> xyz row
-    double extent, s_max;
-    int spc;
-    long np;
-};
 
 // cell c in [0, n-2] with ax[c] <= x < ax[c+1] (clamped at both ends), walking from c
 __device__ __forceinline__ int walk_cell(const double* __restrict__ ax, int n, double x, int c) {
@@ -30,15 +21,6 @@ __device__ __forceinline__ int walk_cell(const double* __restrict__ ax, int n, d
     while (c < n - 2 && x >= __ldg(ax + c + 1)) ++c;
     return c;
 }
-__device__ __forceinline__ int find_cell(const double* __restrict__ ax, int n, double x) {
-    int lo = 0, hi = n - 1;                   // invariant: ax[lo] <= x < ax[hi] (after clamping)
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (x >= __ldg(ax + mid)) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 struct RRay {
     double p[3];      // physical position (frame order)
     double d[3];      // v / c
@@ -157,10 +139,15 @@ __global__ void __launch_bounds__(128) trace_axes_kernel(const typename GridT<T>
                                                          const uint32_t* __restrict__ perm, double* __restrict__ rf,
                                                          double* __restrict__ sf,
                                                          unsigned long long* __restrict__ ray_steps,
-                                                         uint8_t* __restrict__ status, AxesArgs A) {
+                                                         uint8_t* __restrict__ status, AxesArgs A,
+                                                         const unsigned int* __restrict__ any_deferred = nullptr) {
+    // second pass behind trace_axes_event_kernel (any_deferred != null): only the rays it handed over
+    if (any_deferred && *any_deferred == 0u) return;
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned steps = 0;
-    if (tid < A.np) {
+    bool mine = tid < A.np;
+    if (mine && any_deferred) mine = status[perm ? (long)perm[tid] : tid] == TT_RAY_DEFERRED;
+    if (mine) {
         const long ray = perm ? (long)perm[tid] : tid;
         double P[3], D[3], lo[3], hi[3];
 #pragma unroll
@@ -321,6 +308,29 @@ __global__ void __launch_bounds__(128) trace_axes_kernel(const typename GridT<T>
     }
 }
 
+// event marching on a rectilinear grid: one ray per thread, body in trace_axes_event.cuh (host + device)
+template <typename T>
+__global__ void __launch_bounds__(128, 3)
+trace_axes_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0,
+                        const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
+                        unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, AxesArgs A,
+                        unsigned int* __restrict__ any_deferred) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned steps = 0;
+    if (tid < A.np) {
+        const long ray = perm ? (long)perm[tid] : tid;
+        bool deferred = false;
+        steps = axes_event_ray<T>(grid, s0, ray, rf, sf, status, A, deferred);
+        if (deferred) *any_deferred = 1u;           // (benign race: everybody stores 1)
+    }
+    if (ray_steps) {
+        unsigned v = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
+    }
+}
+
 // ElectronCube.dndr on a rectilinear grid: zero outside, faces inclusive (scipy _rgi.py:635-642)
 template <typename T>
 __global__ void dndr_axes_kernel(const typename GridT<T>::V4* __restrict__ grid, AxesArgs A,
@@ -383,12 +393,35 @@ extern "C" int tt_trace_axes(const tt_trace_params* p, const double* x_dev, cons
     const long blocks = (np + block - 1) / block;
     TT_REQUIRE(blocks < (1L << 31), "tt_trace_axes: too many rays for one launch");
     cudaStream_t s = (cudaStream_t)stream;
+    // variant: 0 = auto (event marching when a status buffer is given), 3 = event marching (needs status_dev),
+    //          1 / 2 = the gather kernel alone
+    TT_REQUIRE(p->variant >= 0 && p->variant <= 3, "tt_trace_axes: unknown kernel variant %d", p->variant);
+    TT_REQUIRE(p->variant != 3 || status_dev, "tt_trace_axes: event marching (variant 3) needs status_dev");
+    unsigned int* flag = nullptr;
+    if ((p->variant == 0 || p->variant == 3) && status_dev) {
+        // stream-ordered 4-byte scratch flag: "did the event kernel defer any ray?"
+        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
+            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+            if (p->dtype == TT_F32)
+                trace_axes_event_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                                                  sf_dev, ray_steps_dev, status_dev, A, flag);
+            else
+                trace_axes_event_kernel<double><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev,
+                                                                                   sf_dev, ray_steps_dev, status_dev, A, flag);
+            int rc2 = launch_check("trace_axes_event_kernel");
+            if (rc2) { cudaFreeAsync(flag, s); return rc2; }
+        } else {
+            (void)cudaGetLastError();       // no scratch: the gather kernel does everything
+            flag = nullptr;
+        }
+    }
     if (p->dtype == TT_F32)
         trace_axes_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
-                                                                    ray_steps_dev, status_dev, A);
+                                                                    ray_steps_dev, status_dev, A, flag);
     else
         trace_axes_kernel<double><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
-                                                                     ray_steps_dev, status_dev, A);
+                                                                     ray_steps_dev, status_dev, A, flag);
+    if (flag) cudaFreeAsync(flag, s);
     return launch_check("trace_axes_kernel");
 }
 

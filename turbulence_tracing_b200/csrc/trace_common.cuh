@@ -28,26 +28,48 @@ struct TraceArgs {
                                   // that the second pass can return at once when there is nothing to do
 };
 
+// TT_HD: helpers that also compile for the host, so that the per-ray bodies built from them can be run on
+// the CPU by the test harness (tests/host/: the same source, no GPU needed).  No effect on the device code.
+#define TT_HD __host__ __device__ __forceinline__
+
 template <typename T> struct GridT;
 template <> struct GridT<float> {
     typedef float4 V4;
-    static __device__ __forceinline__ float4 ld(const float4* p) { return __ldg(p); }
+    static TT_HD float4 ld(const float4* p) {
+#ifdef __CUDA_ARCH__
+        return __ldg(p);
+#else
+        return *p;
+#endif
+    }
 };
 template <> struct GridT<double> {
     typedef double4 V4;
-    static __device__ __forceinline__ double4 ld(const double4* p) {
+    static TT_HD double4 ld(const double4* p) {
+#ifdef __CUDA_ARCH__
         const double2* q = reinterpret_cast<const double2*>(p);
         double2 a = __ldg(q), b = __ldg(q + 1);
         return make_double4(a.x, a.y, b.x, b.y);
+#else
+        return *p;
+#endif
     }
 };
+// read-only scalar load (node tables of the rectilinear kernels)
+TT_HD double ldg_f64(const double* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 template <typename T> __device__ __forceinline__ T tfloor(T x);
 template <> __device__ __forceinline__ float tfloor<float>(float x) { return floorf(x); }
 template <> __device__ __forceinline__ double tfloor<double>(double x) { return floor(x); }
-template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
-template <> __device__ __forceinline__ float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
-template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> TT_HD T tfma(T a, T b, T c);
+template <> TT_HD float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> TT_HD double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
 
 // cell/fraction of coordinate (i + f) clamped into [0, n-1]; the upper face is cell n-2, t = 1
 // (as scipy's find_indices does for x == grid[-1]).
@@ -87,6 +109,42 @@ __device__ __forceinline__ G3<T> trilinear(const typename GridT<T>::V4* __restri
     TT_TRI(x) TT_TRI(y) TT_TRI(z)
 #undef TT_TRI
     return g;
+}
+
+// ---- the field of ONE cell as a trilinear polynomial per component (event-marching kernels) ----------
+template <typename T>
+struct Tri {           // trilinear polynomial of one component in one cell
+    T a, b, c, d, a1, b1, c1, d1;
+};
+// evaluation is "w first": the bilinear coefficients at w-fraction fw (4 FMA), then the bilinear form
+// (3 FMA).  RK4 stages 2 and 3 share their w-fraction, so their coefficients are formed once.
+template <typename T>
+struct Bil {
+    T a, b, c, d;
+};
+template <typename T>
+TT_HD Bil<T> tri_at(const Tri<T>& q, T fw) {
+    Bil<T> r;
+    r.a = tfma(fw, q.a1, q.a); r.b = tfma(fw, q.b1, q.b); r.c = tfma(fw, q.c1, q.c); r.d = tfma(fw, q.d1, q.d);
+    return r;
+}
+template <typename T>
+TT_HD T bil_eval(const Bil<T>& q, T tu, T tv) {
+    return tfma(tv, tfma(tu, q.d, q.c), tfma(tu, q.b, q.a));
+}
+// coefficients of plane 0 from its 4 corners; primed = plane 1 minus plane 0
+template <typename T>
+TT_HD void tri_set(Tri<T>& q, T c00, T c10, T c01, T c11, T e00, T e10, T e01, T e11) {
+    q.a = c00; q.b = c10 - c00; q.c = c01 - c00; q.d = (c11 - c01) - q.b;
+    T ea = e00, eb = e10 - e00, ec = e01 - e00, ed = (e11 - e01) - eb;
+    q.a1 = ea - q.a; q.b1 = eb - q.b; q.c1 = ec - q.c; q.d1 = ed - q.d;
+}
+// advance one plane: plane 1 becomes plane 0, (n00..n11) are the corners of the new plane 1
+template <typename T>
+TT_HD void tri_advance(Tri<T>& q, T n00, T n10, T n01, T n11) {
+    q.a += q.a1; q.b += q.b1; q.c += q.c1; q.d += q.d1;
+    T eb = n10 - n00;
+    q.a1 = n00 - q.a; q.b1 = eb - q.b; q.c1 = (n01 - n00) - q.c; q.d1 = ((n11 - n01) - eb) - q.d;
 }
 
 template <typename T>

@@ -33,40 +33,7 @@ namespace tt {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <typename T>
-struct Tri {           // trilinear polynomial of one component in one cell
-    T a, b, c, d, a1, b1, c1, d1;
-};
-// evaluation is "w first": the bilinear coefficients at w-fraction fw (4 FMA), then the bilinear form
-// (3 FMA).  RK4 stages 2 and 3 share their w-fraction, so their coefficients are formed once.
-template <typename T>
-struct Bil {
-    T a, b, c, d;
-};
-template <typename T>
-__device__ __forceinline__ Bil<T> tri_at(const Tri<T>& q, T fw) {
-    Bil<T> r;
-    r.a = tfma(fw, q.a1, q.a); r.b = tfma(fw, q.b1, q.b); r.c = tfma(fw, q.c1, q.c); r.d = tfma(fw, q.d1, q.d);
-    return r;
-}
-template <typename T>
-__device__ __forceinline__ T bil_eval(const Bil<T>& q, T tu, T tv) {
-    return tfma(tv, tfma(tu, q.d, q.c), tfma(tu, q.b, q.a));
-}
-// coefficients of plane 0 from its 4 corners; primed = plane 1 minus plane 0
-template <typename T>
-__device__ __forceinline__ void tri_set(Tri<T>& q, T c00, T c10, T c01, T c11, T e00, T e10, T e01, T e11) {
-    q.a = c00; q.b = c10 - c00; q.c = c01 - c00; q.d = (c11 - c01) - q.b;
-    T ea = e00, eb = e10 - e00, ec = e01 - e00, ed = (e11 - e01) - eb;
-    q.a1 = ea - q.a; q.b1 = eb - q.b; q.c1 = ec - q.c; q.d1 = ed - q.d;
-}
-// advance one plane: plane 1 becomes plane 0, (n00..n11) are the corners of the new plane 1
-template <typename T>
-__device__ __forceinline__ void tri_advance(Tri<T>& q, T n00, T n10, T n01, T n11) {
-    q.a += q.a1; q.b += q.b1; q.c += q.c1; q.d += q.d1;
-    T eb = n10 - n00;
-    q.a1 = n00 - q.a; q.b1 = eb - q.b; q.c1 = (n01 - n00) - q.c; q.d1 = ((n11 - n01) - eb) - q.d;
-}
+// Tri<T> / Bil<T> (the trilinear polynomial of one cell and its evaluation) live in trace_common.cuh.
 
 template <typename T, bool SPC1>
 __global__ void __launch_bounds__(128, sizeof(T) == 8 ? TT_EVENT_MIN_BLOCKS_F64 : TT_EVENT_MIN_BLOCKS)
