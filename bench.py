@@ -399,6 +399,8 @@ def run_gpu_arm(args, wl):
         s0_host.copy_(s0_dev.torch)
         torch.cuda.synchronize()
         cube2 = make_cube()
+        if args.e2e_chunk:
+            cube2.pipeline_chunk_rays = args.e2e_chunk
         ne_np, s0_np = ne_host.numpy(), s0_host.numpy()
 
         e2e_events = []
@@ -430,6 +432,7 @@ def run_gpu_arm(args, wl):
                "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(args.steps, 1),
                "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
                "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),
+               "pipeline_chunk_rays": int(getattr(cube2, "pipeline_chunk_rays", 12_500_000)),
                "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
         del ne_host, s0_host
 
@@ -537,6 +540,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--cpu-rays", type=int, default=1000, help="rays per host process in the CPU baseline sample")
     ap.add_argument("--cube-file", default="", help="(reference arm) .npy ne cube to trace instead of a host GRF")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="rays per upload chunk of the pipelined host-ray path (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
