@@ -138,8 +138,9 @@ def _stretched_case():
     s0[2, 3] = 0.5 * (z[10] + z[11])
     s0[2, 4] = z[-1]
     s0[0, 5], s0[3, 5], s0[5, 5] = x[-1] - 1e-5, 0.2 * C_LIGHT, np.sqrt(1 - 0.04) * C_LIGHT      # side exit
+    s0[2, 5] = z[0]
     s0[5, 6] = -C_LIGHT                                                                           # backward
-    s0[3, 7], s0[5, 7] = 0.8 * C_LIGHT, 0.6 * C_LIGHT                                            # steep
+    s0[3, 7], s0[5, 7], s0[2, 7] = 0.8 * C_LIGHT, 0.6 * C_LIGHT, z[0]                            # steep
     s0[0, 8] = x[-1] + 1e-3                                                                       # misses
     return x, y, z, ne, s0, [1, 5, 6, 7, 8]
 

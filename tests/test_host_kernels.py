@@ -131,8 +131,9 @@ def test_rectilinear_event_body_edge_cases(host_lib):
     s0[2, 4] = z[-1]                               # already on the far face
     special = {5: "side", 6: "backward", 7: "steep", 8: "outside"}
     s0[0, 5], s0[3, 5], s0[5, 5] = x[-1] - 1e-5, 0.2 * C_LIGHT, np.sqrt(1 - 0.04) * C_LIGHT      # leaves through +x
+    s0[2, 5] = z[0]                                # (from the entry face: launched further out it would miss)
     s0[5, 6] = -C_LIGHT                            # flying away
-    s0[3, 7], s0[5, 7] = 0.8 * C_LIGHT, 0.6 * C_LIGHT                                            # d_w < 0.75
+    s0[3, 7], s0[5, 7], s0[2, 7] = 0.8 * C_LIGHT, 0.6 * C_LIGHT, z[0]                            # d_w < 0.75
     s0[0, 8] = x[-1] + 1e-3                        # misses the cube
     ref = orc_c.solve(field, s0, ext, "z", rtol=1e-13, atol=1e-16, batch=1, strict=False)[0]
     G = _grid4(ne, x, y, z, 2, np.float64)
@@ -150,3 +151,109 @@ def test_rectilinear_event_body_edge_cases(host_lib):
     # without an sf buffer
     rf2 = _run(host_lib, G, x, y, z, 2, ext, s0, 8, want_sf=False)[0]
     np.testing.assert_array_equal(rf2[:, marched], rf[:, marched])
+
+
+# ------------------------------------------------------------------------------------------- optics + histogram
+class _Optic(C.Structure):
+    _fields_ = [("op", C.c_int), ("pad_", C.c_int), ("a", C.c_double), ("b", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def optics_lib(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("host") / "optics_host.so")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "turbulence_tracing_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "host", "optics_host.cu"), "-o", out], check=True)
+    lib = C.CDLL(out)
+    vp = C.c_void_p
+    lib.host_optics_hist.argtypes = [vp, C.c_long, C.c_double, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.host_optics_hist.restype = C.c_int
+    return lib
+
+
+def _host_optics(lib, r0_m, program, hist=None, pos_scale=1e3):
+    """element program (the tuples the Python mirror records) on metres/radians rays -> rf (mm / rad) and, with
+    hist = (Lx, Ly, nbx, nby), the histogram (nby, nbx) over numpy.linspace edges as Rays.histogram builds them"""
+    r0_m = np.ascontiguousarray(r0_m, dtype=np.float64)
+    n = r0_m.shape[1]
+    prog = (_Optic * max(1, len(program)))()
+    for k, (code, a, b) in enumerate(program):
+        prog[k].op, prog[k].a, prog[k].b = code, a, b
+    rf = np.empty((4, n))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    H = xe = ye = None
+    nbx = nby = 0
+    if hist is not None:
+        Lx, Ly, nbx, nby = hist
+        xe, ye = np.linspace(-Lx / 2, Lx / 2, nbx + 1), np.linspace(-Ly / 2, Ly / 2, nby + 1)
+        H = np.zeros((nby, nbx), dtype=np.uint64)
+    rc = lib.host_optics_hist(p(r0_m), n, float(pos_scale), C.cast(prog, C.c_void_p), len(program),
+                              p(xe) if H is not None else None, nbx, p(ye) if H is not None else None, nby,
+                              p(H) if H is not None else None, p(rf))
+    assert rc == 0
+    return rf, H
+
+
+def _detector_program(cls, ctor=None, solve=None):
+    """the element program a detector class of the Python mirror records (no GPU involved)"""
+    class Probe:
+        focal_plane, L, R = 0, 400, 25
+        def _set_program(self, prog):
+            self.prog = list(prog)
+    pr = Probe()
+    for k, v in (ctor or {}).items():
+        setattr(pr, k, v)
+    cls.solve(pr, **(solve or {}))
+    return pr.prog
+
+
+def test_optics_kernel_source_reproduces_reference_bit_for_bit(optics_lib, golden):
+    """elements, the four detector programs and numpy.histogram2d binning, from the kernel's own source, against
+    arrays produced by the live reference (4000 rays incl. rejected ones): equal to the last bit"""
+    from turbulence_tracing_b200 import ray_transfer_matrix as rtm
+    g = golden("optics")
+    r0 = g["r0"]
+    one = lambda prog: _host_optics(optics_lib, r0, prog)[0]
+    np.testing.assert_array_equal(one([]), g["m_to_mm"])
+    np.testing.assert_array_equal(one([rtm._op_lens(300.0, 150.0)]), g["lens"])
+    np.testing.assert_array_equal(one([rtm._op_lens(250.0, 250.0)]), g["sym_lens"])
+    np.testing.assert_array_equal(one([rtm._op_distance(123.0)]), g["distance"])
+    np.testing.assert_array_equal(one([rtm._op(rtm._lib.OP_CIRC_APERTURE, 3.0)]), g["circular_aperture"])
+    np.testing.assert_array_equal(one([rtm._op(rtm._lib.OP_CIRC_STOP, 3.0)]), g["circular_stop"])
+    np.testing.assert_array_equal(one(rtm._ops_angular_filter(np.arange(0, 6, 0.5))), g["angular_filter"])
+    np.testing.assert_array_equal(one([rtm._op(rtm._lib.OP_RECT_APERTURE, 2.0, 1.0)]), g["rect_aperture"])
+    np.testing.assert_array_equal(one([rtm._op_knife(0.5, "y", 1)]), g["knife_edge_y_pos"])
+    np.testing.assert_array_equal(one([rtm._op_knife(-0.5, "x", -1)]), g["knife_edge_x_neg"])
+    cases = {
+        "sh": (rtm.Shadowgraphy, dict(L=400, R=25, focal_plane=0), {}, (18, 13.5)),
+        "sh_fp": (rtm.Shadowgraphy, dict(L=400, R=25, focal_plane=5), {}, (6, 6)),
+        "df": (rtm.Schlieren_DF, dict(L=400, R=25), dict(R=3), (6, 6)),
+        "lf": (rtm.Schlieren_LF, dict(L=400, R=25), dict(R=3), (6, 6)),
+        "afr": (rtm.AFR, dict(L=100, R=25, focal_plane=5), dict(Rs=np.arange(0, 6, 0.5)), (15, 10)),
+    }
+    H = {}
+    for k, (cls, ckw, skw, (Lx, Ly)) in cases.items():
+        prog = _detector_program(cls, ckw, skw)
+        rf, H[k] = _host_optics(optics_lib, r0, prog, hist=(Lx, Ly, 3448 // 25, 2574 // 25))
+        np.testing.assert_array_equal(rf, g[k + "_rf"], err_msg=k)
+        np.testing.assert_array_equal(H[k].astype(np.float64), g[k + "_H"], err_msg=k)
+    Hd = _host_optics(optics_lib, r0, _detector_program(rtm.Shadowgraphy), hist=(18, 13.5, 344, 257))[1]
+    np.testing.assert_array_equal(Hd.astype(np.float64), g["sh_default_H"])
+    sh6 = _host_optics(optics_lib, r0, _detector_program(rtm.Shadowgraphy), hist=(6, 6, 3448 // 25, 2574 // 25))[1]
+    np.testing.assert_array_equal(H["df"] + H["lf"], sh6)          # dark field + light field = shadowgraphy
+
+
+def test_histogram_kernel_source_edge_semantics(optics_lib):
+    """numpy.histogram2d: right-open bins, last edge inclusive, NaN and out-of-range dropped"""
+    xe = np.linspace(-9, 9, 345)
+    x = np.r_[xe[0], xe[-1], xe[17], np.nextafter(xe[17], -1), xe[-1] + 1e-12, np.nan, 0.0, 1e-300, -1e-300]
+    y = np.r_[0.0, 6.75, -6.75, 0.1, 0.1, 0.1, np.nan, 0.0, 0.0]
+    r = np.zeros((4, x.size))
+    r[0], r[2] = x, y
+    H = _host_optics(optics_lib, r, [], hist=(18, 13.5, 344, 257), pos_scale=1.0)[1]
+    ok = ~np.isnan(x) & ~np.isnan(y)
+    Href = np.histogram2d(x[ok], y[ok], bins=[344, 257], range=[[-9, 9], [-6.75, 6.75]])[0].T
+    np.testing.assert_array_equal(H.astype(np.float64), Href)

@@ -14,6 +14,27 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned int* scratch_flag(cudaStream_t s) {
+    static bool pool_kept[64] = {};             // per device; a benign race sets the same attribute twice
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_kept[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+        pool_kept[dev] = true;
+    }
+    unsigned int* flag = nullptr;
+    if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+    return flag;
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
     return TT_ERR_CUDA;

@@ -27,10 +27,46 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                \
     } while (0)
 
+// 4-byte stream-ordered scratch word, zeroed (nullptr if the pool cannot serve it).  The device's default memory
+// pool is told ONCE to keep what it has been given (release threshold = max): with the default threshold of 0 the
+// pool hands its memory back to the driver at every synchronisation, and the next cudaMallocAsync has to map
+// fresh physical memory -- milliseconds up to (measured on a B200 VM) hundreds of milliseconds per trace launch.
+unsigned int* scratch_flag(cudaStream_t s);
+
 inline int launch_check(const char* name) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, name);
     return TT_OK;
+}
+
+// TT_HD: helpers that also compile for the host, so that the per-ray bodies built from them can be run on
+// the CPU by the test harness (tests/host/: the same source, no GPU needed).  No effect on the device code.
+#define TT_HD __host__ __device__ __forceinline__
+
+// read-only scalar load (node tables, histogram edges)
+TT_HD double ldg_f64(const double* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// one IEEE operation, never contracted into an FMA (numpy rounds every product and sum)
+TT_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+TT_HD double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
 }
 
 // frame permutation: (u, v, w) = (t1, t2, par) -> index into (x, y, z)

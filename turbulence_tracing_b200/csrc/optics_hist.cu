@@ -10,78 +10,13 @@
 // increment is a shared-memory atomic and the window is flushed once with one global atomic per
 // non-empty bin.  Rays outside the window fall through to a global atomic (unordered beams: ~4e10
 // atomics/s on B200, still faster than a permuted gather of the rays -- see ray_transfer_matrix.py).
-#include "common.cuh"
+#include "optics_program.cuh"      // OpticsArgs, apply_program, bin_of (host + device)
 
 namespace tt {
 
 static constexpr int kThreads = 256;
 static constexpr int kRaysPerThread = 8;
 static constexpr int kTile = 64;
-
-struct OpticsArgs {
-    tt_optic ops[TT_MAX_OPTICS];
-    int n_ops;
-    double pos_scale;
-    int nbx, nby;
-    long np;
-};
-
-// numpy semantics (searchsorted side='right', last edge inclusive): bin b holds e[b] <= x < e[b+1],
-// x == e[nb] goes to bin nb-1, anything else (incl. NaN) is dropped (returns -1).
-__device__ __forceinline__ int bin_of(double x, const double* __restrict__ e, int nb) {
-    const double lo = __ldg(e), hi = __ldg(e + nb);
-    if (!(x >= lo && x <= hi)) return -1;
-    int b = (int)((x - lo) * ((double)nb / (hi - lo)));
-    b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
-    while (b > 0 && x < __ldg(e + b)) --b;
-    while (b < nb - 1 && x >= __ldg(e + b + 1)) ++b;
-    return b;
-}
-
-// r^2 exactly as numpy evaluates r[0]**2 + r[2]**2 (two rounded products, one rounded sum)
-__device__ __forceinline__ double radius2(double x, double y) {
-    return __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
-}
-
-__device__ __forceinline__ void apply_program(const OpticsArgs& A, double& x, double& th, double& y, double& ph) {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int i = 0; i < A.n_ops; ++i) {
-        const tt_optic o = A.ops[i];
-        bool reject = false;
-        switch (o.op) {
-            case TT_OP_DISTANCE:        // [[1, d], [0, 1]] on (x, theta) and (y, phi)
-                x = fma(o.a, th, x);
-                y = fma(o.a, ph, y);
-                break;
-            case TT_OP_LENS:            // [[1, 0], [-1/f, 1]]
-                th = __dadd_rn(__dmul_rn(-1.0 / o.a, x), th);
-                ph = __dadd_rn(__dmul_rn(-1.0 / o.b, y), ph);
-                break;
-            case TT_OP_CIRC_APERTURE:
-                reject = radius2(x, y) > __dmul_rn(o.a, o.a);
-                break;
-            case TT_OP_CIRC_STOP:
-                reject = radius2(x, y) < __dmul_rn(o.a, o.a);
-                break;
-            case TT_OP_ANNULAR_STOP: {
-                const double rr = radius2(x, y);
-                reject = rr > __dmul_rn(o.a, o.a) && rr < __dmul_rn(o.b, o.b);
-                break;
-            }
-            case TT_OP_RECT_APERTURE:   // rejects only rays outside in BOTH axes (:132-135)
-                reject = __dmul_rn(x, x) > __dmul_rn(o.a, o.a) && __dmul_rn(y, y) > __dmul_rn(o.b, o.b);
-                break;
-            case TT_OP_KNIFE_EDGE: {
-                const double c = (o.b == 1.0 || o.b == -1.0) ? x : y;
-                reject = o.b > 0 ? (c > o.a) : (c < o.a);
-                break;
-            }
-            default: break;
-        }
-        // a 4x4 matmul spreads a NaN over all four rows; rejected rays are NaN columns (:78)
-        if (reject || x != x || th != th || y != y || ph != ph) { x = th = y = ph = nan; }
-    }
-}
 
 __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __restrict__ rf_in,
                                                                const uint32_t* __restrict__ perm,

@@ -503,13 +503,8 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     unsigned int* flag = nullptr;
     if (variant >= 3) {
         // stream-ordered 4-byte scratch flag: "did the event kernel defer any ray?"
-        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
-            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
-            A.any_deferred = flag;
-        } else {
-            (void)cudaGetLastError();
-            flag = nullptr;
-        }
+        flag = scratch_flag(s);
+        A.any_deferred = flag;
         // event marching (packed FP32x2 arithmetic for variant 3 in FP32), then the second pass below
         int rc2 = launch_trace_event(p->dtype, variant == 3, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, nullptr, nullptr, AuxArgs(), s);
@@ -556,13 +551,8 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
     int only_flagged = 0;
     unsigned int* flag = nullptr;
     if (p->dtype == TT_F32 && status_dev && (p->variant == 0 || p->variant == 3)) {
-        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
-            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
-            A.any_deferred = flag;
-        } else {
-            (void)cudaGetLastError();
-            flag = nullptr;
-        }
+        flag = scratch_flag(s);
+        A.any_deferred = flag;
         // event marching with the passive quantities on board; the gather kernel then redoes the deferred rays
         int rc2 = launch_trace_event(TT_F32, true, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, aux4_dev, aux_out_dev, AX, s);

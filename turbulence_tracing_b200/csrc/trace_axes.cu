@@ -400,8 +400,8 @@ extern "C" int tt_trace_axes(const tt_trace_params* p, const double* x_dev, cons
     unsigned int* flag = nullptr;
     if ((p->variant == 0 || p->variant == 3) && status_dev) {
         // stream-ordered 4-byte scratch flag: "did the event kernel defer any ray?"
-        if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) == cudaSuccess) {
-            cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+        flag = scratch_flag(s);
+        if (flag) {         // (no scratch: the gather kernel does everything)
             if (p->dtype == TT_F32)
                 trace_axes_event_kernel<float><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4_dev, s0_dev, perm_dev, rf_dev,
                                                                                   sf_dev, ray_steps_dev, status_dev, A, flag);
@@ -410,9 +410,6 @@ extern "C" int tt_trace_axes(const tt_trace_params* p, const double* x_dev, cons
                                                                                    sf_dev, ray_steps_dev, status_dev, A, flag);
             int rc2 = launch_check("trace_axes_event_kernel");
             if (rc2) { cudaFreeAsync(flag, s); return rc2; }
-        } else {
-            (void)cudaGetLastError();       // no scratch: the gather kernel does everything
-            flag = nullptr;
         }
     }
     if (p->dtype == TT_F32)

@@ -28,10 +28,6 @@ struct TraceArgs {
                                   // that the second pass can return at once when there is nothing to do
 };
 
-// TT_HD: helpers that also compile for the host, so that the per-ray bodies built from them can be run on
-// the CPU by the test harness (tests/host/: the same source, no GPU needed).  No effect on the device code.
-#define TT_HD __host__ __device__ __forceinline__
-
 template <typename T> struct GridT;
 template <> struct GridT<float> {
     typedef float4 V4;
@@ -55,14 +51,6 @@ template <> struct GridT<double> {
 #endif
     }
 };
-// read-only scalar load (node tables of the rectilinear kernels)
-TT_HD double ldg_f64(const double* p) {
-#ifdef __CUDA_ARCH__
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
 
 template <typename T> __device__ __forceinline__ T tfloor(T x);
 template <> __device__ __forceinline__ float tfloor<float>(float x) { return floorf(x); }

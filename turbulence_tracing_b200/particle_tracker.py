@@ -493,12 +493,13 @@ class ElectronCube:
             copy.wait_stream(main)
             # the first chunks are short (chunk/8, /4, /2) so that tracing starts ~1.5 ms after the first byte
             # instead of after a whole chunk's upload (12 ms at PCIe 5 rates)
+            growth = int(getattr(self, "pipeline_growth", 2))
             bounds, lo, n = [], 0, max(chunk // 8, 1)
             while lo < Np:
                 n = min(n, Np - lo)
                 bounds.append((lo, n))
                 lo += n
-                n = min(2 * n, chunk)
+                n = min(growth * n, chunk)
             for ci, (lo, n) in enumerate(bounds):
                 b = ci % 2
                 with torch.cuda.stream(copy):
