@@ -179,3 +179,20 @@ def test_c_threads_and_bundling_do_not_change_results(golden):
     assert nfev == 2 + 6 * (ns + nr)               # f0, the initial-step probe, 6 per attempted step
     empty = orc_c.solve(field, np.zeros((6, 0)), float(g["extent"]), "z")
     assert empty[0].shape == (4, 0) and empty[2] == 0
+
+
+def test_c_oracle_reports_scipys_crawl_instead_of_hanging():
+    """a ray launched exactly ON the far face with v = c (the reference's probing_direction='x' beam):
+    at tight tolerances solve_ivp never gets off the face (x + v h rounds back onto it, the field jumps there) and
+    crawls in ~1e-27 s steps; the restatement follows it step for step and gives up after TTO_MAX_ATTEMPTS"""
+    x = np.linspace(-5e-3, 5e-3, 21)
+    ne = orc.density("exponential_cos", x, x, x, n_e0=3e24, Ly=2e-3, s=4e-3)
+    field = orc_c.make_field(ne, x, x, x)
+    s0 = np.array([[5e-3, -2.29220346e-3, 9.38656709e-4, orc.C_LIGHT, 39.8, 1.4858e4],
+                   [5e-3, 1e-3, 1e-3, 0.999 * orc.C_LIGHT, 0.0, 0.04 * orc.C_LIGHT]]).T
+    rf, sf, _ = orc_c.solve(field, s0, 5e-3, "x", rtol=1e-13, atol=1e-16, batch=1, strict=False)
+    assert np.all(np.isnan(sf[:, 0])) and np.all(np.isfinite(sf[:, 1]))
+    with pytest.raises(RuntimeError):
+        orc_c.solve(field, s0[:, :1], 5e-3, "x", rtol=1e-13, atol=1e-16, batch=1)
+    # at the reference's default tolerances the same ray is no problem
+    assert np.all(np.isfinite(orc_c.solve(field, s0, 5e-3, "x")[0]))

@@ -341,12 +341,13 @@ __device__ __forceinline__ void clamp_in(int& i, T& f, int n) {
 }
 
 
-template <typename T> __device__ __forceinline__ T trcp(T x);
+template <typename T> TT_HD T trcp(T x);
 #ifndef TT_RCP_NEWTON
 #define TT_RCP_NEWTON 0     // measured on B200 (513^3, 1e8 rays): 442.5 ms with the Newton step, 426.8 ms without; the
                             // 2^-23 relative error of MUFU.RCP moves exit positions by ~1e-11 m (tolerance 5e-8 m)
 #endif
-template <> __device__ __forceinline__ float trcp<float>(float x) {
+template <> TT_HD float trcp<float>(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
 #if TT_RCP_NEWTON
@@ -354,8 +355,11 @@ template <> __device__ __forceinline__ float trcp<float>(float x) {
 #else
     return r;                                    // MUFU.RCP alone: max relative error 2^-23
 #endif
+#else
+    return 1.0f / x;                             // host run of the kernel source (tests/host/)
+#endif
 }
-template <> __device__ __forceinline__ double trcp<double>(double x) { return 1.0 / x; }
+template <> TT_HD double trcp<double>(double x) { return 1.0 / x; }
 
 
 struct AuxArgs {
