@@ -140,11 +140,12 @@ int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* g
  * bisection (particle_tracker.py:235-241).  These entry points are the same three operations with the
  * node coordinates x_dev[nx], y_dev[ny], z_dev[nz] (device, FP64, strictly ascending) instead of
  * origin + spacing; grid layout, outputs, status flags and ray order are those of tt_calc_dndr /
- * tt_trace / tt_dndr.  tt_trace_axes ignores p->origin_xyz and p->spacing_xyz; its arithmetic is FP64
- * whatever the grid's element type.  p->variant: 0 = auto / 3 = event marching in index space with the
- * sizes of the current cell (needs status_dev; every RK4 step inside one cell, corners loaded once per
- * cell), followed by the gather kernel on the rays it defers (outside / steep / side exit / time cap);
- * 1, 2 = the gather kernel alone (cell search by walking at every stage). */
+ * tt_trace / tt_dndr.  tt_trace_axes ignores p->origin_xyz and p->spacing_xyz.  p->variant: 0 = auto /
+ * 3 = event marching in index space with the sizes of the current cell (needs status_dev; every RK4 step
+ * inside one cell, corners loaded once per cell; state and arithmetic in the grid's element type, launch
+ * and exit in FP64), followed by the gather kernel on the rays it defers (outside / steep / side exit /
+ * time cap); 1, 2 = the gather kernel alone (FP64 arithmetic whatever the grid's type, cell search by
+ * walking at every stage). */
 int tt_calc_dndr_axes(const void* ne_dev, int ne_dtype, const int n_xyz[3], const double* x_dev,
                       const double* y_dev, const double* z_dev, int par, double nc, double ne_max,
                       void* grid4_dev, int grid_dtype, tt_stream_t stream);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python scripts/bench_rectilinear.py > gpurun_out/bench_rectilinear.log 2>&1; cat gpurun_out/bench_rectilinear.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_axes_event -c 1 -o gpurun_out/r01_trace_axes_event python scripts/bench_rectilinear.py --one > gpurun_out/ncu_rect.log 2>&1; tail -3 gpurun_out/ncu_rect.log
+ncu -i gpurun_out/r01_trace_axes_event.ncu-rep --page raw --csv > gpurun_out/r01_trace_axes_event_raw.csv 2>/dev/null; wc -c gpurun_out/r01_trace_axes_event_raw.csv

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(128) trace_axes_kernel(const typename GridT<T>
 
 // event marching on a rectilinear grid: one ray per thread, body in trace_axes_event.cuh (host + device)
 template <typename T>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, sizeof(T) == 8 ? 3 : 4)
 trace_axes_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0,
                         const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
                         unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, AxesArgs A,

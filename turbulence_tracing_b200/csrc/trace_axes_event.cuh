@@ -33,8 +33,9 @@ TT_HD int find_cell(const double* __restrict__ ax, int n, double x) {
 // with the sizes (h_u, h_v, h_w) of the CURRENT cell -- three values refreshed from the node tables whenever
 // the ray is relabelled into a neighbouring cell (plane arrival: h_w; u / v face: h_u / h_v).  Every RK4 step
 // lies inside one cell (no kink of the field is straddled), no stage needs a cell search, and the eight
-// corners are loaded once per cell.  State and arithmetic are FP64 whatever the grid's element type, like the
-// gather kernel of trace_axes.cu, which stays the second pass for everything unusual (launched outside the cube beside
+// corners are loaded once per cell.  State and arithmetic have the grid's element type (FP32 for a float4 grid:
+// positions are (cell, fraction) pairs, so the resolution is 6e-8 of a cell; launch and exit go through FP64);
+// the FP64 gather kernel of trace_axes.cu stays the second pass for everything unusual (launched outside the cube beside
 // the entry face, steep / backward, side exit, possible time cap, non-finite): those rays are flagged
 // TT_RAY_DEFERRED and redone from s0.
 // Returns the (sub-)plane arrivals of this ray (0 if deferred).
@@ -43,7 +44,7 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
                               double* __restrict__ rf, double* __restrict__ sf, uint8_t* __restrict__ status,
                               const AxesArgs& A, bool& deferred) {
     typedef typename GridT<T>::V4 V4;
-    typedef double R;
+    typedef T R;              // arithmetic follows the grid: FP32 state for a float4 grid (positions stay (cell, fraction))
     unsigned steps = 0;
     const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
     const size_t plane = (size_t)nu * nv;
@@ -100,7 +101,7 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
         load_cell();
         while (true) {
             // ---- stage 1 and the length of this step (in w-cell fractions) -------------------------
-            R q = R(1) / dw, hq = hw * q;
+            R q = trcp<R>(dw), hq = hw * q;
             bool ok = dw > R(TT_MARCH_MIN_DW);
             const R aU = ru * du * q, aV = rv * dv * q;
             const R adu = bil_eval<R>(tri_at<R>(qx, fw), tu, tv) * hq, adv = bil_eval<R>(tri_at<R>(qy, fw), tu, tv) * hq,
@@ -125,20 +126,20 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
             // ---- stages 2-4 -------------------------------------------------------------------------
             R su = fma(half, aU, tu), sv = fma(half, aV, tv), sw = fw + half;
             R du2 = fma(half, adu, du), dv2 = fma(half, adv, dv), dw2 = fma(half, adw, dw);
-            q = R(1) / dw2; hq = hw * q; ok = ok && dw2 > R(0);
+            q = trcp<R>(dw2); hq = hw * q; ok = ok && dw2 > R(0);
             const R bU = ru * du2 * q, bV = rv * dv2 * q;
             const Bil<R> mx = tri_at<R>(qx, sw), my = tri_at<R>(qy, sw), mz = tri_at<R>(qz, sw);   // stages 2 and 3
             const R bdu = bil_eval<R>(mx, su, sv) * hq, bdv = bil_eval<R>(my, su, sv) * hq,
                     bdw = bil_eval<R>(mz, su, sv) * hq, bs = hq;
             su = fma(half, bU, tu); sv = fma(half, bV, tv);
             du2 = fma(half, bdu, du); dv2 = fma(half, bdv, dv); dw2 = fma(half, bdw, dw);
-            q = R(1) / dw2; hq = hw * q; ok = ok && dw2 > R(0);
+            q = trcp<R>(dw2); hq = hw * q; ok = ok && dw2 > R(0);
             const R cU = ru * du2 * q, cV = rv * dv2 * q;
             const R cdu = bil_eval<R>(mx, su, sv) * hq, cdv = bil_eval<R>(my, su, sv) * hq,
                     cdw = bil_eval<R>(mz, su, sv) * hq, cs = hq;
             su = fma(h, cU, tu); sv = fma(h, cV, tv); sw = fw + h;
             du2 = fma(h, cdu, du); dv2 = fma(h, cdv, dv); dw2 = fma(h, cdw, dw);
-            q = R(1) / dw2; hq = hw * q; ok = ok && dw2 > R(0);
+            q = trcp<R>(dw2); hq = hw * q; ok = ok && dw2 > R(0);
             const R eU = ru * du2 * q, eV = rv * dv2 * q;
             const R edu = bil_eval<R>(tri_at<R>(qx, sw), su, sv) * hq, edv = bil_eval<R>(tri_at<R>(qy, sw), su, sv) * hq,
                     edw = bil_eval<R>(tri_at<R>(qz, sw), su, sv) * hq, es = hq;
@@ -190,15 +191,16 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
         steps = 0;
     } else {
         // ---- epilogue: ray_at_exit (particle_tracker.py:345-380) and the state at time T ---------
-        const double Pu = fma((double)tu, (double)hu, xu0), Pv = fma((double)tv, (double)hv, xv0), Pw = hi[2];
-        const double Vu = du * kC, Vv = dv * kC, Vw = dw * kC;
+        const double Pu = fma((double)tu, ldg_f64(axu + cu + 1) - xu0, xu0), Pv = fma((double)tv, ldg_f64(axv + cv + 1) - xv0, xv0);
+        const double Pw = hi[2];
+        const double Vu = (double)du * kC, Vv = (double)dv * kC, Vw = (double)dw * kC;
         const double tb = (Pw - A.extent) / Vw;
         rf[0 * A.np + ray] = Pu - Vu * tb;
         rf[1 * A.np + ray] = atan(Vu / Vw);
         rf[2 * A.np + ray] = Pv - Vv * tb;
         rf[3 * A.np + ray] = atan(Vv / Vw);
         if (sf) {
-            const double t_rest = (A.s_max - s_pre - s) / kC;
+            const double t_rest = (A.s_max - s_pre - (double)s) / kC;
             const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
