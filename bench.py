@@ -432,7 +432,8 @@ def run_gpu_arm(args, wl):
                "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(args.steps, 1),
                "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
                "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),
-               "pipeline_chunk_rays": int(getattr(cube2, "pipeline_chunk_rays", 50_000_000)),
+               "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
+                            "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None)},
                "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
         del ne_host, s0_host
 

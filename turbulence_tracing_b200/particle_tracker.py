@@ -480,14 +480,17 @@ class ElectronCube:
                     torch.empty((3, n), dtype=torch.float64, device="cuda") if use_aux else None)
 
         # ---- host rays: H2D copies of chunk i+1 overlap the trace of chunk i (two streams) --------------------
-        # Chunk sizes grow geometrically (first, 3 first, 9 first, ... capped): tracing starts ~1.5 ms after the first
-        # byte, every upload hides behind the trace of the previous chunk (0.9 ns vs 4.2 ns per ray at PCIe 5 rates),
-        # and most rays travel in a few large chunks -- a chunk is a random 1/k sample of the beam, and the fewer
-        # rays share a cell column the lower the L1 reuse of the trace kernel (measured on B200, 513^3 / 1e8 rays:
-        # 12.5 M-ray chunks 452.7 ms, 1.56 / 4.7 / 14 / 42 / 37.7 M 441.6 ms, device-resident rays 422.5 ms).
-        cap = max(int(getattr(self, "pipeline_chunk_rays", 50_000_000)), 1)
+        # Chunk sizes grow geometrically (first, g first, g^2 first, ... capped): tracing starts ~1.5 ms after the first
+        # byte, every upload hides behind the trace of the previous chunk, and most rays travel in a few large chunks --
+        # a chunk is a random 1/k sample of the beam, and the fewer rays share a cell column the lower the L1 reuse
+        # of the trace kernel (measured on B200, 513^3 / 1e8 rays: 12.5 M-ray chunks 452.7 ms, 1.56 / 4.7 / 14 / 42 /
+        # 37.7 M 441.6 ms, device-resident rays 422.5 ms).  How fast the chunks may grow depends on the upload rate
+        # (0.9 ns per ray at 55 GB/s against 4.2 ns of tracing; with 8 ranks uploading at once a B200 box gives each
+        # ~20 GB/s), so the rate of the FIRST chunk decides the schedule unless the caller fixed it.
+        cap_user = getattr(self, "pipeline_chunk_rays", None)
+        growth_user = getattr(self, "pipeline_growth", None)
+        cap = max(int(cap_user or 50_000_000), 1)
         first = max(int(getattr(self, "pipeline_first_rays", min(1_562_500, max(cap // 8, 1)))), 1)
-        growth = max(int(getattr(self, "pipeline_growth", 3)), 1)
         if host and Np >= 2 * first:
             src = torch.from_numpy(np.ascontiguousarray(self._s0[:6], dtype=np.float64))
             rf, sf, status, aux_out = outputs(Np)
@@ -495,25 +498,25 @@ class ElectronCube:
             main = torch.cuda.current_stream()
             copy = getattr(self, "_copy_stream", None) or torch.cuda.Stream()
             self._copy_stream = copy
-            bounds, lo, n = [], 0, first
+            free = [None, None]                            # compute-done events per buffer
+            bufs = [None, None]
+            copy.wait_stream(main)
+            lo, n, ci, growth = 0, first, 0, None
             while lo < Np:
                 n = min(n, Np - lo)
-                bounds.append((lo, n))
-                lo += n
-                n = min(growth * n, cap)
-            chunk = max(n for _, n in bounds)
-            bufs = [torch.empty((6, chunk), dtype=torch.float64, device="cuda") for _ in range(2)]
-            free = [None, None]                            # compute-done events per buffer
-            copy.wait_stream(main)
-            for ci, (lo, n) in enumerate(bounds):
                 b = ci % 2
+                if bufs[b] is None or bufs[b].shape[1] < n:    # (allocated on the main stream, like the outputs)
+                    bufs[b] = torch.empty((6, n), dtype=torch.float64, device="cuda")
                 with torch.cuda.stream(copy):
                     if free[b] is not None:
                         copy.wait_event(free[b])
-                    s0b = bufs[b][:, :n] if n == chunk else bufs[b].reshape(-1)[:6 * n].view(6, n)
+                    s0b = bufs[b] if n == bufs[b].shape[1] else bufs[b].reshape(-1)[:6 * n].view(6, n)
+                    if ci == 0:
+                        t_start = torch.cuda.Event(enable_timing=True)
+                        t_start.record(copy)
                     for r in range(6):
                         s0b[r].copy_(src[r, lo:lo + n], non_blocking=True)
-                    ready = torch.cuda.Event()
+                    ready = torch.cuda.Event(enable_timing=(ci == 0))
                     ready.record(copy)
                 main.wait_event(ready)
                 rf_c, sf_c, st_c, ax_c = outputs(n)
@@ -528,6 +531,19 @@ class ElectronCube:
                     perm[lo:lo + n] = pc + lo              # global ray ids, chunk after chunk
                 free[b] = torch.cuda.Event()
                 free[b].record(main)
+                if growth is None:                         # after the first chunk: pick the schedule
+                    growth = int(growth_user) if growth_user else 0
+                    if not growth:
+                        ready.synchronize()                # ~1.5 ms; the GPU is busy tracing the first chunk meanwhile
+                        gbs = 48.0 * n / max(t_start.elapsed_time(ready), 1e-3) * 1e-6
+                        self.last_upload_gbs = gbs
+                        growth = 3 if gbs >= 35.0 else 2
+                        if not cap_user:
+                            cap = 50_000_000 if gbs >= 35.0 else (25_000_000 if gbs >= 15.0 else 12_500_000)
+                    growth = max(growth, 1)
+                lo += n
+                ci += 1
+                n = min(growth * n, cap)
             init_aux = _lib.to_device(self._s0[6:9], torch.float64) if shape0[0] == 9 else None
         else:
             s0 = _lib.to_device(self._s0, torch.float64)
