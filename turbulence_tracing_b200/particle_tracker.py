@@ -505,11 +505,15 @@ class ElectronCube:
             while lo < Np:
                 n = min(n, Np - lo)
                 b = ci % 2
-                if bufs[b] is None or bufs[b].shape[1] < n:    # (allocated on the main stream, like the outputs)
-                    bufs[b] = torch.empty((6, n), dtype=torch.float64, device="cuda")
                 with torch.cuda.stream(copy):
                     if free[b] is not None:
                         copy.wait_event(free[b])
+                    if bufs[b] is None or bufs[b].shape[1] < n:
+                        # staging buffers live in the COPY stream's pool: memory recycled there was last used by
+                        # copy-stream work (ordered before this copy), never by a main-stream kernel that may
+                        # still be running; the trace kernels read them on the main stream, hence record_stream
+                        bufs[b] = torch.empty((6, n), dtype=torch.float64, device="cuda")
+                        bufs[b].record_stream(main)
                     s0b = bufs[b] if n == bufs[b].shape[1] else bufs[b].reshape(-1)[:6 * n].view(6, n)
                     if ci == 0:
                         t_start = torch.cuda.Event(enable_timing=True)
