@@ -23,6 +23,9 @@ namespace tt {
 #ifndef TT_EVENT_MIN_BLOCKS
 #define TT_EVENT_MIN_BLOCKS 5        // FP32: 95 registers, no spills -> 20 warps / SM
 #endif
+#ifndef TT_EVENT_MIN_BLOCKS_AUX
+#define TT_EVENT_MIN_BLOCKS_AUX 3    // passive quantities on board: four packed polynomials, 168 registers
+#endif
 #ifndef TT_EVENT_MIN_BLOCKS_F64
 #define TT_EVENT_MIN_BLOCKS_F64 3
 #endif
@@ -113,7 +116,7 @@ __device__ __forceinline__ void aux_integrands(float nn, f32x2 bxy, f32x2 bzk, f
 
 // CUBIC: h_u = h_v = h_w, so the index-space slopes need no rescaling (x * 1.0f is exact: same bits).
 template <bool SPC1, bool AUX, bool CUBIC>
-__global__ void __launch_bounds__(128, AUX ? 3 : TT_EVENT_MIN_BLOCKS)
+__global__ void __launch_bounds__(128, AUX ? TT_EVENT_MIN_BLOCKS_AUX : TT_EVENT_MIN_BLOCKS)
 trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
                          const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
                          unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A,
