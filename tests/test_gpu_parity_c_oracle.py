@@ -226,3 +226,38 @@ def test_rectilinear_event_marching_beam_against_c_oracle(tt):
         else:
             assert p <= 1e-3 * PIXEL_M
     print(f"event marching vs gather on the rectilinear grid: {ms[('float64', 2)] / ms[('float64', 0)]:.1f}x")
+
+
+@pytest.mark.parametrize("rectilinear", [False, True])
+def test_non_finite_and_resting_launch_rays_do_not_disturb_the_bundle(tt, golden, rectilinear):
+    """NaN / inf positions or velocities and a ray at rest (v = 0: it never leaves, the reference integrates it to the
+    time cap): the kernels must terminate, flag nothing as marched that was not, and leave every other ray of the
+    bundle bit-identical.  (scipy's solve_ivp would abort the WHOLE bundle on a NaN; here the damage stays local.)"""
+    g = golden("trace_grf33")
+    x = g["x"] if not rectilinear else g["x"] + 2e-5 * np.sin(np.linspace(0, 7, g["x"].size))
+    x = np.sort(x)
+    s0 = g["s0"][:, :64].copy()
+    bad = {3: (0, np.nan), 7: (5, np.nan), 11: (1, np.inf), 19: (3, -np.inf)}
+    dirty = s0.copy()
+    for ray, (row, val) in bad.items():
+        dirty[row, ray] = val
+    dirty[:, 23] = 0.0                                               # at rest in the middle of the cube
+    out = {}
+    for name, rays in (("clean", s0), ("dirty", dirty)):
+        cube = tt.particle_tracker.ElectronCube(x, x, x, dtype="float32", steps_per_cell=2, verbose=False)
+        cube.external_ne(g["ne"])
+        cube.calc_dndr()
+        assert (cube._nodes is not None) == rectilinear
+        cube.s0 = rays
+        cube.extent = float(g["extent"])
+        out[name] = (np.asarray(cube.solve()), np.asarray(cube.status), np.asarray(cube.sf))
+    good = np.ones(64, bool)
+    good[list(bad) + [23]] = False
+    np.testing.assert_array_equal(out["dirty"][0][:, good], out["clean"][0][:, good])
+    np.testing.assert_array_equal(out["dirty"][1][good], out["clean"][1][good])
+    np.testing.assert_array_equal(out["dirty"][2][:, good], out["clean"][2][:, good])
+    st = out["dirty"][1]
+    assert not np.any(st == 0xFF)                                    # nothing left in the internal "deferred" state
+    for ray in bad:
+        assert not np.all(np.isfinite(out["dirty"][0][:, ray])), ray  # garbage in, NaN out -- never a plausible ray
+    assert st[23] & 4 and not (st[23] & 1)                           # the resting ray ran into the time cap
