@@ -272,12 +272,17 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
         int st = 0;
         double s_acc = 0.0;     // path time spent before/inside the cube
         // ---- prologue: free flight to the cube if launched outside ------------------------------
-        bool inside = true;
+        // (a NaN / inf launch state is "a ray that misses": fmin / fmax below would drop the NaN and turn it
+        //  into a plausible ray; as MISSED its non-finite values reach rf untouched)
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) finite = finite && isfinite(P[k]) && isfinite(D[k]);
+        bool inside = finite;
 #pragma unroll
         for (int k = 0; k < 3; ++k) inside = inside && X[k] >= 0.0 && X[k] <= (double)(A.n[k] - 1);
         if (!inside) {
             double t_in = 0.0, t_out = 1e300;
-            bool hit = true;
+            bool hit = finite;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 double rate = D[k] / A.h[k], hi = (double)(A.n[k] - 1);

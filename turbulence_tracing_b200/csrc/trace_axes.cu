@@ -162,12 +162,16 @@ __global__ void __launch_bounds__(128) trace_axes_kernel(const typename GridT<T>
 #pragma unroll
         for (int k = 0; k < 3; ++k) { r.p[k] = P[k]; r.d[k] = D[k]; }
         // ---- prologue: free flight to the cube if launched outside ----------------------------------
-        bool inside = true;
+        // (a NaN / inf launch state is "a ray that misses": see trace.cu)
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) finite = finite && isfinite(P[k]) && isfinite(D[k]);
+        bool inside = finite;
 #pragma unroll
         for (int k = 0; k < 3; ++k) inside = inside && P[k] >= lo[k] && P[k] <= hi[k];
         if (!inside) {
             double t_in = 0.0, t_out = 1e300;
-            bool hit = true;
+            bool hit = finite;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 if (D[k] == 0.0) {
