@@ -1,14 +1,12 @@
-// TEST HARNESS (not product): runs the per-ray body of the uniform-grid event-marching kernels
-// (csrc/trace_event_ray.cuh -- tt_trace variant 4, and variant 3 in FP64; the packed FP32x2 production kernel
-// performs the same operations in the same order) on the HOST for tests/test_host_kernels.py.
+// TEST HARNESS (not product): runs the per-ray bodies of the uniform-grid event-marching kernels
+// (csrc/trace_event_ray.cuh: event_ray -- tt_trace variant 4, and variant 3 in FP64 -- and event_ray_f32x2, the
+// packed FP32x2 production kernel, whose PTX instructions are emulated lane by lane) on the HOST for
+// tests/test_host_kernels.py.
 #include "trace_event_ray.cuh"
 
-extern "C" int host_trace_event(const void* grid4, int dtype, const int n_xyz[3], const double origin_xyz[3],
-                                const double spacing_xyz[3], int par, double extent, double s_max, int spc,
-                                const double* s0, long np, double* rf, double* sf, unsigned char* status,
-                                unsigned long long* ray_steps, long* n_deferred) {
+static void fill(tt::TraceArgs& A, const int n_xyz[3], const double origin_xyz[3], const double spacing_xyz[3], int par,
+                 double extent, double s_max, int spc, long np) {
     using namespace tt;
-    TraceArgs A;
     Frame f = frame_of(par);
     for (int k = 0; k < 3; ++k) {
         A.fa[k] = f.a[k]; A.n[k] = n_xyz[f.a[k]]; A.o[k] = origin_xyz[f.a[k]]; A.h[k] = spacing_xyz[f.a[k]];
@@ -17,6 +15,50 @@ extern "C" int host_trace_event(const void* grid4, int dtype, const int n_xyz[3]
     A.plane_elems = (long long)A.n[0] * A.n[1];
     A.hwf = (float)A.h[2]; A.ruf = (float)(A.h[2] / A.h[0]); A.rvf = (float)(A.h[2] / A.h[1]);
     A.extent = extent; A.s_max = s_max; A.spc = spc; A.np = np;
+}
+
+// the production kernel's body (packed FP32x2 arithmetic, emulated lane by lane on the host), as launch_trace_event
+// dispatches it; aux4 / aux_out non-null: the tt_trace_aux variant with the passive quantities on board
+extern "C" int host_trace_event_packed(const void* grid4, const int n_xyz[3], const double origin_xyz[3],
+                                       const double spacing_xyz[3], int par, double extent, double s_max, int spc,
+                                       const double* s0, long np, double* rf, double* sf, unsigned char* status,
+                                       unsigned long long* ray_steps, long* n_deferred, const void* aux4,
+                                       double* aux_out, double omega_over_c, double verdet_nc, int with_aux) {
+    using namespace tt;
+    TraceArgs A;
+    fill(A, n_xyz, origin_xyz, spacing_xyz, par, extent, s_max, spc, np);
+    AuxArgs AX;
+    AX.omega_over_c = omega_over_c; AX.verdet_nc = verdet_nc;
+    const bool spc1 = spc == 1, cubic = A.ruf == 1.0f && A.rvf == 1.0f;
+    const float4* g = (const float4*)grid4;
+    const float4* b = (const float4*)aux4;
+    unsigned long long steps = 0;
+    long nd = 0;
+    for (long ray = 0; ray < np; ++ray) {
+        bool d = false;
+#define TT_CALL(S1, AX_, CU) event_ray_f32x2<S1, AX_, CU>(g, s0, ray, rf, sf, status, A, b, aux_out, AX, d)
+        if (with_aux) {
+            if (spc1) steps += cubic ? TT_CALL(true, true, true) : TT_CALL(true, true, false);
+            else steps += cubic ? TT_CALL(false, true, true) : TT_CALL(false, true, false);
+        } else {
+            if (spc1) steps += cubic ? TT_CALL(true, false, true) : TT_CALL(true, false, false);
+            else steps += cubic ? TT_CALL(false, false, true) : TT_CALL(false, false, false);
+        }
+#undef TT_CALL
+        nd += d;
+    }
+    *ray_steps = steps;
+    *n_deferred = nd;
+    return 0;
+}
+
+extern "C" int host_trace_event(const void* grid4, int dtype, const int n_xyz[3], const double origin_xyz[3],
+                                const double spacing_xyz[3], int par, double extent, double s_max, int spc,
+                                const double* s0, long np, double* rf, double* sf, unsigned char* status,
+                                unsigned long long* ray_steps, long* n_deferred) {
+    using namespace tt;
+    TraceArgs A;
+    fill(A, n_xyz, origin_xyz, spacing_xyz, par, extent, s_max, spc, np);
     unsigned long long steps = 0;
     long nd = 0;
     for (long ray = 0; ray < np; ++ray) {
