@@ -3,6 +3,7 @@
 // packed FP32x2 production kernel, whose PTX instructions are emulated lane by lane) on the HOST for
 // tests/test_host_kernels.py.
 #include "trace_event_ray.cuh"
+#include "trace_gather_ray.cuh"
 
 static void fill(tt::TraceArgs& A, const int n_xyz[3], const double origin_xyz[3], const double spacing_xyz[3], int par,
                  double extent, double s_max, int spc, long np) {
@@ -71,6 +72,50 @@ extern "C" int host_trace_event(const void* grid4, int dtype, const int n_xyz[3]
                               : event_ray<double, false>((const double4*)grid4, s0, ray, rf, sf, status, A, deferred);
         }
         nd += deferred;
+    }
+    *ray_steps = steps;
+    *n_deferred = nd;
+    return 0;
+}
+
+// tt_trace as the library dispatches it, on the host: variant 0 / 3 = event marching (packed FP32x2 body for float
+// grids, scalar body for double) followed by the gather kernel's body on the rays it deferred; 1 = 8-corner gather at
+// every stage; 2 = cell cache.  with_aux: the tt_trace_aux entry (gather variant 1 with the passive quantities).
+extern "C" int host_trace(const void* grid4, int dtype, int variant, const int n_xyz[3], const double origin_xyz[3],
+                          const double spacing_xyz[3], int par, double extent, double s_max, int spc,
+                          const double* s0, long np, double* rf, double* sf, unsigned char* status,
+                          unsigned long long* ray_steps, long* n_deferred) {
+    using namespace tt;
+    TraceArgs A;
+    fill(A, n_xyz, origin_xyz, spacing_xyz, par, extent, s_max, spc, np);
+    const AuxArgs AX = AuxArgs();
+    const bool spc1 = spc == 1, cubic = A.ruf == 1.0f && A.rvf == 1.0f;
+    unsigned long long steps = 0;
+    long nd = 0;
+    for (long ray = 0; ray < np; ++ray) {
+        bool d = false;
+        if (variant == 0 || variant == 3) {
+            if (dtype == TT_F32) {
+                const float4* g = (const float4*)grid4;
+#define TT_CALL(S1, CU) event_ray_f32x2<S1, false, CU>(g, s0, ray, rf, sf, status, A, nullptr, nullptr, AX, d)
+                if (spc1) steps += cubic ? TT_CALL(true, true) : TT_CALL(true, false);
+                else steps += cubic ? TT_CALL(false, true) : TT_CALL(false, false);
+#undef TT_CALL
+            } else {
+                steps += spc1 ? event_ray<double, true>((const double4*)grid4, s0, ray, rf, sf, status, A, d)
+                              : event_ray<double, false>((const double4*)grid4, s0, ray, rf, sf, status, A, d);
+            }
+            if (!d) continue;
+            ++nd;
+            if (dtype == TT_F32) steps += gather_ray<float, 0, false>((const float4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+            else steps += gather_ray<double, 0, false>((const double4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+        } else if (variant == 1) {
+            if (dtype == TT_F32) steps += gather_ray<float, 1, false>((const float4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+            else steps += gather_ray<double, 1, false>((const double4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+        } else {
+            if (dtype == TT_F32) steps += gather_ray<float, 0, false>((const float4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+            else steps += gather_ray<double, 0, false>((const double4*)grid4, s0, ray, rf, sf, status, A, nullptr, nullptr, AX);
+        }
     }
     *ray_steps = steps;
     *n_deferred = nd;

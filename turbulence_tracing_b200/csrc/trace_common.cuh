@@ -52,9 +52,9 @@ template <> struct GridT<double> {
     }
 };
 
-template <typename T> __device__ __forceinline__ T tfloor(T x);
-template <> __device__ __forceinline__ float tfloor<float>(float x) { return floorf(x); }
-template <> __device__ __forceinline__ double tfloor<double>(double x) { return floor(x); }
+template <typename T> TT_HD T tfloor(T x);
+template <> TT_HD float tfloor<float>(float x) { return floorf(x); }
+template <> TT_HD double tfloor<double>(double x) { return floor(x); }
 template <typename T> TT_HD T tfma(T a, T b, T c);
 template <> TT_HD float tfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> TT_HD double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -62,7 +62,7 @@ template <> TT_HD double tfma<double>(double a, double b, double c) { return fma
 // cell/fraction of coordinate (i + f) clamped into [0, n-1]; the upper face is cell n-2, t = 1
 // (as scipy's find_indices does for x == grid[-1]).
 template <typename T>
-__device__ __forceinline__ void cell_of(int i, T f, int n, int& c, T& t) {
+TT_HD void cell_of(int i, T f, int n, int& c, T& t) {
     T fl = tfloor(f);
     c = i + (int)fl;
     t = f - fl;
@@ -74,7 +74,7 @@ template <typename T> struct G3 { T x, y, z; };
 
 // trilinear gradient in cell (cu, cv, cw) at fractions (tu, tv, tw)
 template <typename T>
-__device__ __forceinline__ G3<T> trilinear(const typename GridT<T>::V4* __restrict__ grid, int nu,
+TT_HD G3<T> trilinear(const typename GridT<T>::V4* __restrict__ grid, int nu,
                                            size_t plane, int cu, int cv, int cw, T tu, T tv, T tw) {
     typedef typename GridT<T>::V4 V4;
     const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
@@ -167,7 +167,7 @@ struct AuxCtx {
 };
 
 template <typename T>
-__device__ __forceinline__ void trilinear_w(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
+TT_HD void trilinear_w(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
                                             int cu, int cv, int cw, T tu, T tv, T tw, T& w_only) {
     typedef typename GridT<T>::V4 V4;
     const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
@@ -181,7 +181,7 @@ __device__ __forceinline__ void trilinear_w(const typename GridT<T>::V4* __restr
 }
 
 template <typename T>
-__device__ __forceinline__ void trilinear4(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
+TT_HD void trilinear4(const typename GridT<T>::V4* __restrict__ grid, int nu, size_t plane,
                                            int cu, int cv, int cw, T tu, T tv, T tw, T& x, T& y, T& z, T& w) {
     typedef typename GridT<T>::V4 V4;
     const V4* p = grid + ((size_t)cw * plane + (size_t)cv * nu + cu);
@@ -204,7 +204,7 @@ __device__ __forceinline__ void trilinear4(const typename GridT<T>::V4* __restri
 
 // integrands at one stage, multiplied by `scale` (ds/dW = hw/dw when marching in W, 1 in path time)
 template <typename T>
-__device__ __forceinline__ void aux_rates(const AuxCtx<T>& ctx, const typename GridT<T>::V4* __restrict__ grid,
+TT_HD void aux_rates(const AuxCtx<T>& ctx, const typename GridT<T>::V4* __restrict__ grid,
                                           const Consts<T>& C, int cu, int cv, int cw, T tu, T tv, T tw, T du, T dv,
                                           T dw, T scale, double& fp, double& ff, double& fa) {
     T nn;
@@ -223,7 +223,7 @@ __device__ __forceinline__ void aux_rates(const AuxCtx<T>& ctx, const typename G
 // One RK4 step in W from fraction fwa to fwa + h inside w-cell k (0 <= fwa, fwa + h <= 1).
 // Updates fu, fv (un-normalised), d and s of r.  Returns false if a stage saw d_w <= 0.
 template <typename T, bool AUX = false>
-__device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+TT_HD bool zstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
                                       Ray<T>& r, int k, T fwa, T h, AuxCtx<T>* ctx = nullptr) {
     const T half = T(0.5) * h;
     int cu, cv; T tu, tv;
@@ -282,7 +282,7 @@ __device__ __forceinline__ bool zstep(const typename GridT<T>::V4* __restrict__ 
 
 // One RK4 step of length ds in path time (general direction).  Fractions un-normalised after.
 template <typename T, bool AUX = false>
-__device__ __forceinline__ void sstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
+TT_HD void sstep(const typename GridT<T>::V4* __restrict__ grid, const Consts<T>& C,
                                       Ray<T>& r, T ds, AuxCtx<T>* ctx = nullptr) {
     const T half = T(0.5) * ds;
     int cu, cv, cw; T tu, tv, tw;
@@ -319,7 +319,7 @@ __device__ __forceinline__ void sstep(const typename GridT<T>::V4* __restrict__ 
 
 // fraction of the chord old -> new at which coordinate (i + f) leaves [0, n-1]; 2 if it does not
 template <typename T>
-__device__ __forceinline__ T leave_fraction(int i, T f_old, T f_new, int n) {
+TT_HD T leave_fraction(int i, T f_old, T f_new, int n) {
     T lo = T(-i), hi = T(n - 1 - i);
     if (f_new < lo) return (lo - f_old) / (f_new - f_old);
     if (f_new > hi) return (hi - f_old) / (f_new - f_old);
@@ -327,14 +327,14 @@ __device__ __forceinline__ T leave_fraction(int i, T f_old, T f_new, int n) {
 }
 
 template <typename T>
-__device__ __forceinline__ void renorm(int& i, T& f) {
+TT_HD void renorm(int& i, T& f) {
     T fl = tfloor(f);
     i += (int)fl;
     f -= fl;
 }
 // snap a coordinate that should lie on/inside the faces back into [0, n-1]
 template <typename T>
-__device__ __forceinline__ void clamp_in(int& i, T& f, int n) {
+TT_HD void clamp_in(int& i, T& f, int n) {
     renorm(i, f);
     if (i < 0) { i = 0; f = T(0); }
     if (i > n - 1 || (i == n - 1 && f > T(0))) { i = n - 1; f = T(0); }
