@@ -562,3 +562,66 @@ def test_whole_trace_on_the_host_over_critical_liner(trace_lib, golden):
     assert ok.sum() >= 8
     np.testing.assert_allclose(rf[1][ok], g["rf"][1][ok], rtol=0, atol=2e-4)
     np.testing.assert_allclose(rf[0][ok], g["rf"][0][ok], rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------- Gaussian random fields
+@pytest.fixture(scope="module")
+def grf_lib(tmp_path_factory):
+    lib = _build_host(tmp_path_factory, "grf_host")
+    vp = C.c_void_p
+    lib.host_grf_spectrum.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_ulonglong, vp]
+    lib.host_grf_spectrum.restype = C.c_int
+    return lib
+
+
+def _host_grf(lib, ndim, N, k_func, Wr=None, Wi=None, seed=0):
+    """half spectrum from the kernel's per-mode function, inverse transform by numpy (cuFFT's C2R is unnormalised:
+    the 1/M^ndim of numpy's ifftn sits in the amplitudes, numpy's irfftn divides once more)"""
+    from turbulence_tracing_b200.turboGen import _sqrt_spectrum_table
+    M = 2 * N + 1
+    lut = _sqrt_spectrum_table(N, k_func)
+    lead = (M,) * (ndim - 1)
+    F = np.zeros(lead + (N + 1, 2))
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    Wr = None if Wr is None else np.ascontiguousarray(Wr, dtype=np.float64)
+    Wi = None if Wi is None else np.ascontiguousarray(Wi, dtype=np.float64)
+    assert lib.host_grf_spectrum(ndim, N, p(lut), p(Wr), p(Wi), seed, p(F)) == 0
+    Fc = F[..., 0] + 1j * F[..., 1]
+    return np.fft.irfftn(Fc, s=(M,) * ndim, axes=tuple(range(ndim))) * float(M) ** ndim, Fc
+
+
+def test_grf_spectrum_kernel_source_reproduces_reference_fields(grf_lib, golden):
+    """turboGen.gaussian{1,2,3}D_FFT (turboGen.py:388-538): the kernel's Hermitian half spectrum, built from the
+    reference's own white-noise draws (np.random.randn in its order) and inverse-transformed, equals the reference's
+    field to rounding"""
+    g = golden("grf")
+    spec = lambda k: k ** (-11.0 / 3.0)
+    for nd in (1, 2, 3):
+        N = int(g[f"N{nd}"])
+        M = 2 * N + 1
+        np.random.seed(30 + nd)
+        Wr = np.random.randn(*((M,) * nd))
+        Wi = np.random.randn(*((M,) * nd))
+        f, Fc = _host_grf(grf_lib, nd, N, spec, Wr, Wi)
+        ref = g[f"f{nd}"]
+        assert f.shape == ref.shape
+        np.testing.assert_allclose(f, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+        assert Fc[(0,) * nd] == 0                                    # zero mean
+
+
+def test_grf_philox_mode_is_hermitian_and_has_the_requested_spectrum(grf_lib):
+    """the counter-based generator (seeded mode): the field is real by construction (F(-k) = conj F(k) on the stored
+    c = 0 plane), zero-mean, and its shell-averaged spectrum follows k^-11/3"""
+    N, M = 24, 49
+    f, Fc = _host_grf(grf_lib, 3, N, lambda k: k ** (-11.0 / 3.0), seed=1234)
+    idx = (-np.arange(M)) % M
+    np.testing.assert_allclose(Fc[:, :, 0], np.conj(Fc[idx][:, idx][:, :, 0]), rtol=0, atol=1e-18)
+    assert abs(f.mean()) < 1e-12 * f.std()
+    f2, _ = _host_grf(grf_lib, 3, N, lambda k: k ** (-11.0 / 3.0), seed=1235)
+    assert np.abs(f - f2).max() > 0.1 * f.std()                      # another seed, another field
+    P = np.abs(np.fft.fftn(f)) ** 2
+    k = np.fft.fftfreq(M)
+    K = np.sqrt(k[:, None, None] ** 2 + k[None, :, None] ** 2 + k[None, None, :] ** 2)
+    sel = (K > 0.06) & (K < 0.4)
+    slope = np.polyfit(np.log(K[sel]), np.log(P[sel]), 1)[0]
+    assert abs(slope + 11.0 / 3.0) < 0.15

@@ -5,59 +5,22 @@
 // construction (W = Wr + flip(Wr) + i (Wi - flip(Wi)), :525-528) -- and cuFFT runs one
 // complex-to-real inverse transform.  sqrt(P(|k|)) comes from a table indexed by the integer
 // q = fa^2 + fb^2 + fc^2 (|k| = sqrt(q)/M), evaluated once on the host from the user's k_func.
-#include "common.cuh"
+#include "grf_mode.cuh"
 
 #include <cufft.h>
 
 namespace tt {
 
-template <typename T> struct Cplx;
-template <> struct Cplx<float> { typedef float2 type; };
-template <> struct Cplx<double> { typedef double2 type; };
-
-__device__ __forceinline__ void philox_normals(uint64_t idx, uint64_t seed, double& wr, double& wi) {
-    const double two_pi = 6.283185307179586476925;
-    Philox p = philox4x32_10(idx, 0x47524621ull /* 'GRF!' */, seed);
-    Philox q = philox4x32_10(idx, 0x47524622ull, seed);
-    wr = sqrt(-2.0 * log(u01(p.c[0], p.c[1]))) * cos(two_pi * u01(p.c[2], p.c[3]));
-    wi = sqrt(-2.0 * log(u01(q.c[0], q.c[1]))) * cos(two_pi * u01(q.c[2], q.c[3]));
-}
-
-// one thread per element of the half spectrum (a, b, c), c = 0..N
+// one thread per element of the half spectrum (a, b, c), c = 0..N; the element itself: grf_mode.cuh (host + device)
 template <typename T>
 __global__ void __launch_bounds__(256) grf_spectrum_kernel(int N, int Ma, int Mb, const double* __restrict__ lut,
                                                            const double* __restrict__ Wr,
                                                            const double* __restrict__ Wi, uint64_t seed,
                                                            double norm, typename Cplx<T>::type* __restrict__ F) {
-    // Ma, Mb: extent of the two leading axes (M for a 3-D field; 1 for the axes a 1-D / 2-D field lacks)
-    const int M = 2 * N + 1, Nh = N + 1;
-    const size_t total = (size_t)Ma * Mb * Nh;
+    const size_t total = (size_t)Ma * Mb * (N + 1);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i % Nh);
-    const int b = (int)((i / Nh) % Mb);
-    const int a = (int)(i / ((size_t)Nh * Mb));
-    const int Na = Ma == 1 ? 0 : N, Nb = Mb == 1 ? 0 : N;
-    // signed frequencies of FFT-order indices
-    const int fa = a <= Na ? a : a - Ma, fb = b <= Nb ? b : b - Mb, fc = c;
-    // index of +k and of -k in the fftshift-ed arrays Wr, Wi (:520-526)
-    const size_t jp = ((size_t)(Na + fa) * Mb + (Nb + fb)) * M + (N + fc);
-    const size_t jm = ((size_t)(Na - fa) * Mb + (Nb - fb)) * M + (N - fc);
-    double wrp, wip, wrm, wim;
-    if (Wr) {
-        wrp = Wr[jp]; wrm = Wr[jm]; wip = Wi[jp]; wim = Wi[jm];
-    } else {
-        philox_normals(jp, seed, wrp, wip);
-        philox_normals(jm, seed, wrm, wim);
-    }
-    const int q = fa * fa + fb * fb + fc * fc;
-    // F[0,0,0] = 0 (:534); numpy's ifftn normalisation 1/M^3 (:536) is folded into the amplitude
-    const double amp = q == 0 ? 0.0 : lut[q] * norm;
-    typename Cplx<T>::type o;
-    o.x = (T)((wrp + wrm) * amp);
-    o.y = (T)((wip - wim) * amp);
-    if (q == 0) { o.x = T(0); o.y = T(0); }
-    F[i] = o;
+    F[i] = grf_mode<T>(i, N, Ma, Mb, lut, Wr, Wi, seed, norm);
 }
 
 static int cufft_fail(cufftResult r, const char* what) {
