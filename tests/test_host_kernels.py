@@ -625,3 +625,79 @@ def test_grf_philox_mode_is_hermitian_and_has_the_requested_spectrum(grf_lib):
     sel = (K > 0.06) & (K < 0.4)
     slope = np.polyfit(np.log(K[sel]), np.log(P[sel]), 1)[0]
     assert abs(slope + 11.0 / 3.0) < 0.15
+
+
+# ------------------------------------------------------------------------------------------- calc_dndr
+@pytest.fixture(scope="module")
+def dndr_lib(tmp_path_factory):
+    lib = _build_host(tmp_path_factory, "calc_dndr_host")
+    vp = C.c_void_p
+    lib.host_calc_dndr.argtypes = [vp, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_double * 3), vp, vp, vp, C.c_int,
+                                   C.c_double, C.c_double, vp, C.c_int]
+    lib.host_calc_dndr.restype = C.c_int
+    return lib
+
+
+def _host_calc_dndr(lib, ne, x, y, z, par, ne_max=1.0, lwl=1053e-9, out_dtype=np.float64, rectilinear=False):
+    """replay of the calc_dndr_kernel launch -> dict(dndx, dndy, dndz, ne_nc) unpacked from the interleaved grid"""
+    from oracle import ref_numpy as orc
+    ne = np.ascontiguousarray(ne)
+    assert ne.dtype in (np.float32, np.float64)
+    nc = orc.critical_density(lwl)[1]
+    fa = FRAME[par]
+    G = np.full(tuple(ne.shape[a] for a in (fa[2], fa[1], fa[0])) + (4,), np.nan, dtype=out_dtype)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    h = (C.c_double * 3)(*[(a[-1] - a[0]) / (len(a) - 1) for a in (x, y, z)])
+    ax = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z)]
+    rc = lib.host_calc_dndr(p(ne), 0 if ne.dtype == np.float32 else 1, C.byref((C.c_int * 3)(*ne.shape)), C.byref(h),
+                            p(ax[0]) if rectilinear else None, p(ax[1]) if rectilinear else None,
+                            p(ax[2]) if rectilinear else None, par, float(nc), float(ne_max), p(G),
+                            0 if out_dtype == np.float32 else 1)
+    assert rc == 0 and not np.isnan(G).any()
+    back = np.argsort([fa[2], fa[1], fa[0]])             # grid axes (w, v, u) -> (x, y, z)
+    comp = {}
+    for k, name in enumerate(("dndx", "dndy", "dndz")):
+        comp[name] = G[..., fa.index(k)].transpose(back).astype(np.float64) * C_LIGHT**2
+    comp["ne_nc"] = G[..., 3].transpose(back).astype(np.float64)
+    return comp, G
+
+
+@pytest.mark.parametrize("par", [2, 1, 0])
+def test_calc_dndr_kernel_source_matches_reference(dndr_lib, golden, par):
+    """the stencil kernel replayed block by block: tile transposition, frame permutation, faces, clip -- against the
+    arrays of the live reference (numpy.gradient + the -c^2/2 factor) on a cubic and a 12 x 10 x 14 cube"""
+    g = golden("calc_dndr_uniform")
+    out, G = _host_calc_dndr(dndr_lib, g["ne"], g["x"], g["x"], g["x"], par)
+    for name in ("ne_nc", "dndx", "dndy", "dndz"):
+        np.testing.assert_allclose(out[name], g[name], rtol=0, atol=1e-11 * np.abs(g[name]).max(), err_msg=name)
+    # the same grid as the oracle-based builder the trace tests use
+    np.testing.assert_allclose(G, _grid4(g["ne"], g["x"], g["x"], g["x"], par, np.float64), rtol=0, atol=1e-11 * np.abs(G).max())
+    g = golden("calc_dndr")                               # non-cubic, ne_max = 0.5 with values above the clip
+    x = np.linspace(g["x"][0], g["x"][-1], 12)
+    y = np.linspace(g["y"][0], g["y"][-1], 10)
+    z = np.linspace(g["z"][0], g["z"][-1], 14)
+    out, _ = _host_calc_dndr(dndr_lib, g["ne"], x, y, z, par, ne_max=float(g["ne_max"]), lwl=float(g["lwl"]))
+    assert out["ne_nc"].max() == 0.5
+    for name in ("ne_nc", "dndx", "dndy", "dndz"):
+        np.testing.assert_allclose(out[name], g[name], rtol=0, atol=1e-11 * np.abs(g[name]).max(), err_msg=name)
+
+
+@pytest.mark.parametrize("par", [2, 1, 0])
+def test_calc_dndr_kernel_source_rectilinear_and_fp32(dndr_lib, golden, par):
+    """numpy's non-uniform second-order stencil from per-block coefficient tables (29 x 33 x 37 stretched mesh of the
+    live reference), and the FP32-in / FP32-out path on sizes that are not multiples of the 32-voxel tiles"""
+    g = golden("trace_rectilinear")
+    out, _ = _host_calc_dndr(dndr_lib, g["ne"], g["x"], g["y"], g["z"], par, rectilinear=True)
+    sub = (slice(None, None, 2),) * 3
+    for name in ("dndx", "dndy", "dndz"):
+        ref = g[name + "_sub"]
+        np.testing.assert_allclose(out[name][sub], ref, rtol=0, atol=1e-11 * np.abs(ref).max(), err_msg=name)
+    from oracle import ref_numpy as orc
+    rng = np.random.RandomState(9)
+    x, y, z = np.linspace(-3e-3, 3e-3, 45), np.linspace(-2e-3, 2e-3, 70), np.linspace(-4e-3, 4e-3, 37)
+    ne = (1.2e27 * rng.rand(45, 70, 37)).astype(np.float32)
+    ref = orc.calc_dndr(ne.astype(np.float64), x, y, z, 1053e-9, 0.7)
+    out, _ = _host_calc_dndr(dndr_lib, ne, x, y, z, par, ne_max=0.7, out_dtype=np.float32)
+    assert abs(out["ne_nc"].max() - 0.7) < 1e-7
+    for name in ("ne_nc", "dndx", "dndy", "dndz"):
+        np.testing.assert_allclose(out[name], ref[name], rtol=0, atol=3e-7 * np.abs(ref[name]).max(), err_msg=name)
