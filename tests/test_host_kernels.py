@@ -701,3 +701,42 @@ def test_calc_dndr_kernel_source_rectilinear_and_fp32(dndr_lib, golden, par):
     assert abs(out["ne_nc"].max() - 0.7) < 1e-7
     for name in ("ne_nc", "dndx", "dndy", "dndz"):
         np.testing.assert_allclose(out[name], ref[name], rtol=0, atol=3e-7 * np.abs(ref[name]).max(), err_msg=name)
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs[0], whole chain
+@pytest.mark.parametrize("dtype,spc", [(np.float32, 1), (np.float64, 2)])
+def test_c1_whole_chain_from_kernel_sources_on_the_host(dndr_lib, trace_lib, optics_lib, golden, dtype, spc):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): 100^3 test_exponential_cos cube, seed-0 beam, the four
+    detectors.  Every stage runs the source of the kernel the B200 runs -- calc_dndr (launch replayed block by block),
+    tt_trace (event marching with the packed production body in FP32 + second pass), the fused optics + histogram
+    kernel's per-ray code -- and the result is compared with the reference's own output for the same 1024 rays.
+    Same bounds as the GPU suite: exit position within 1e-3 pixel (FP32) / 1e-5 of the beam radius (FP64),
+    L1(H - H_ref) / sum(H_ref) <= 2/1024 per detector."""
+    from oracle import ref_numpy as orc
+    from turbulence_tracing_b200 import ray_transfer_matrix as rtm
+    g = golden("c1_expcos100")
+    x = np.linspace(-5e-3, 5e-3, 100)
+    ne = orc.density("exponential_cos", x, x, x, n_e0=2e23, Ly=1e-3, s=4e-3)
+    _, G = _host_calc_dndr(dndr_lib, ne.astype(dtype), x, x, x, 2, out_dtype=dtype)
+    np.random.seed(0)
+    s0 = orc.init_beam(1024, 4e-3, 0.05e-3, 5e-3, "z")
+    np.testing.assert_array_equal(s0, g["s0"])
+    rf, sf, st, steps, nd = _run_trace(trace_lib, G, x, x, x, 2, 5e-3, s0, spc)
+    assert np.all(st == EXIT_FACE) and nd == 0 and steps == spc * 99 * 1024
+    pos, ang = _errors(rf, g["rf"])
+    print(f"C1 on the host, {np.dtype(dtype).name} spc={spc}: pos err {pos:.2e} m ({pos / 52.3e-6:.1e} pixel), angle {ang:.1e} of rms")
+    assert pos <= (1e-3 * 52.3e-6 if dtype == np.float32 else 1e-5 * 4e-3)
+    assert ang <= (1e-4 if dtype == np.float32 else 1e-5)
+    dets = {"sh": (rtm.Shadowgraphy, {}), "df": (rtm.Schlieren_DF, dict(R=1)), "lf": (rtm.Schlieren_LF, dict(R=1)),
+            "afr": (rtm.AFR, dict(Rs=np.arange(0, 6, .5)))}
+    for k, (cls, skw) in dets.items():
+        det_rf, H = _host_optics(optics_lib, rf, _detector_program(cls, None, skw), hist=(18, 13.5, 344, 257))
+        Href = np.zeros((257, 344))
+        Href[g[k + "_idx"][0], g[k + "_idx"][1]] = g[k + "_cnt"]
+        l1 = np.abs(H.astype(np.float64) - Href).sum() / max(Href.sum(), 1)
+        print(f"   {k}: accepted {int(H.sum())} / ref {int(Href.sum())}, L1 = {l1:.2e}")
+        assert l1 <= 2 / 1024
+        ok = ~np.isnan(g[k + "_rf"][0])
+        assert np.mean(np.isnan(det_rf[0]) == ~ok) > 0.998
+        both = ok & ~np.isnan(det_rf[0])
+        np.testing.assert_allclose(det_rf[0][both], g[k + "_rf"][0][both], rtol=0, atol=1e-3 * 52.3e-3)
