@@ -740,3 +740,84 @@ def test_c1_whole_chain_from_kernel_sources_on_the_host(dndr_lib, trace_lib, opt
         assert np.mean(np.isnan(det_rf[0]) == ~ok) > 0.998
         both = ok & ~np.isnan(det_rf[0])
         np.testing.assert_allclose(det_rf[0][both], g[k + "_rf"][0][both], rtol=0, atol=1e-3 * 52.3e-3)
+
+
+# ------------------------------------------------------------------------------------------- launch rays, Morton keys
+@pytest.fixture(scope="module")
+def rays_lib(tmp_path_factory):
+    lib = _build_host(tmp_path_factory, "rays_host")
+    vp = C.c_void_p
+    lib.host_init_beam.argtypes = [C.c_long, C.c_long, C.c_ulonglong, C.c_double, C.c_double, C.c_double, C.c_int, vp]
+    lib.host_init_beam.restype = C.c_int
+    lib.host_morton_keys.argtypes = [vp, C.c_long, C.c_int, C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 3),
+                                     C.POINTER(C.c_int * 3), vp]
+    lib.host_morton_keys.restype = C.c_int
+    return lib
+
+
+def _host_beam(lib, n, first, seed, beam, div, extent, par):
+    s0 = np.full((6, n), np.nan)
+    assert lib.host_init_beam(n, first, seed, beam, div, extent, par, s0.ctypes.data_as(C.c_void_p)) == 0
+    return s0
+
+
+def test_device_beam_generator_source_distribution_and_sharding(rays_lib):
+    """tt_init_beam (counter RNG) from its source: the reference's distribution (particle_tracker.py:273-309: radius
+    with pdf 2u on the disc radius, azimuth of the divergence in [0, pi), Gaussian divergence, |v| = c, launch plane
+    per direction incl. the 'x' quirk) and the property the multi-GPU driver relies on: any shard [first, first + n)
+    of ONE global beam is the same whoever generates it"""
+    n, beam, div, ext = 200_000, 4e-3, 2e-3, 5e-3
+    s0 = _host_beam(rays_lib, n, 0, 99, beam, div, ext, 2)
+    r = np.hypot(s0[0], s0[1]) / beam
+    assert r.max() <= 1.0 and abs(r.mean() - 2 / 3) < 3e-3 and abs((r**2).mean() - 0.5) < 3e-3        # pdf 2u
+    np.testing.assert_array_equal(s0[2], -ext)
+    v = np.sqrt((s0[3:] ** 2).sum(axis=0))
+    np.testing.assert_allclose(v, C_LIGHT, rtol=1e-15)
+    assert abs(np.hypot(s0[3], s0[4]).std() / C_LIGHT - div * np.sqrt(1 - 2 / np.pi)) < 0.02 * div   # |N(0, div)|
+    # chi = div * N(0,1) (signed), azimuth phi in [0, pi): v2 = c sin(chi) sin(phi) has the sign of chi
+    assert abs(np.mean(np.sign(s0[4]))) < 0.01 and abs(np.mean(s0[3])) < 0.01 * div * C_LIGHT
+    # shards
+    a = _host_beam(rays_lib, 1000, 5000, 99, beam, div, ext, 2)
+    np.testing.assert_array_equal(a, s0[:, 5000:6000])
+    assert np.abs(_host_beam(rays_lib, 1000, 5000, 100, beam, div, ext, 2) - a).max() > 0             # another seed
+    # probing directions: same draws, permuted rows; 'x' launches at +extent (reference quirk, :280-289)
+    y = _host_beam(rays_lib, 1000, 0, 99, beam, div, ext, 1)
+    x = _host_beam(rays_lib, 1000, 0, 99, beam, div, ext, 0)
+    z = s0[:, :1000]
+    np.testing.assert_array_equal(y[[0, 2, 1, 3, 5, 4]], z)
+    np.testing.assert_array_equal(x[[1, 2, 0, 4, 5, 3]][[0, 1, 3, 4, 5]], z[[0, 1, 3, 4, 5]])
+    np.testing.assert_array_equal(x[0], ext)
+
+
+def test_morton_key_source(rays_lib):
+    """Z-order keys of tt_sort_rays: 16 bits per transverse axis interleaved, clamped outside the cube, NaN -> 0;
+    sorting by the key groups rays by cell column"""
+    x = np.linspace(-5e-3, 5e-3, 33)
+    n = 4096
+    rng = np.random.RandomState(0)
+    s0 = np.zeros((6, n))
+    s0[0], s0[1] = rng.uniform(-6e-3, 6e-3, n), rng.uniform(-6e-3, 6e-3, n)
+    s0[0, 0], s0[1, 1] = np.nan, np.inf
+    keys = np.zeros(n, dtype=np.uint32)
+    org = (C.c_double * 3)(x[0], x[0], x[0])
+    h = (C.c_double * 3)(*([x[1] - x[0]] * 3))
+    assert rays_lib.host_morton_keys(s0.ctypes.data_as(C.c_void_p), n, 2, C.byref(org), C.byref(h),
+                                     C.byref((C.c_int * 3)(33, 33, 33)), keys.ctypes.data_as(C.c_void_p)) == 0
+    def deinterleave(k):
+        k = k & 0x55555555
+        k = (k | (k >> 1)) & 0x33333333
+        k = (k | (k >> 2)) & 0x0F0F0F0F
+        k = (k | (k >> 4)) & 0x00FF00FF
+        k = (k | (k >> 8)) & 0x0000FFFF
+        return k
+    qu, qv = deinterleave(keys), deinterleave(keys >> 1)
+    with np.errstate(invalid="ignore"):
+        eu = np.clip((s0[0] - x[0]) * 65536.0 / 1e-2, 0, 65535)
+        ev = np.clip((s0[1] - x[0]) * 65536.0 / 1e-2, 0, 65535)
+    eu[0] = 0                                                       # NaN -> 0
+    np.testing.assert_array_equal(qu, np.nan_to_num(eu, posinf=65535).astype(np.uint32))
+    np.testing.assert_array_equal(qv, np.nan_to_num(ev, posinf=65535).astype(np.uint32))
+    order = np.argsort(keys, kind="stable")
+    cell = (np.clip(np.floor((s0[0] - x[0]) / (x[1] - x[0])), 0, 31) * 32 + np.clip(np.floor((s0[1] - x[0]) / (x[1] - x[0])), 0, 31))[order]
+    changes = np.count_nonzero(np.diff(cell[2:]))                   # (skipping the two non-finite rays)
+    assert changes < 2 * 1024                                       # ~1 change per occupied column, not per ray
