@@ -121,3 +121,16 @@ extern "C" int host_trace(const void* grid4, int dtype, int variant, const int n
     *n_deferred = nd;
     return 0;
 }
+
+// tt_dndr (ElectronCube.dndr): pos, out: (3, npts) in xyz row order
+extern "C" int host_dndr(const void* grid4, int dtype, const int n_xyz[3], const double origin_xyz[3],
+                         const double spacing_xyz[3], int par, const double* pos, long npts, double* out) {
+    using namespace tt;
+    TraceArgs A;
+    fill(A, n_xyz, origin_xyz, spacing_xyz, par, 0.0, 0.0, 1, npts);
+    for (long i = 0; i < npts; ++i) {
+        if (dtype == TT_F32) dndr_point<float>((const float4*)grid4, A, pos, npts, i, out);
+        else dndr_point<double>((const double4*)grid4, A, pos, npts, i, out);
+    }
+    return 0;
+}

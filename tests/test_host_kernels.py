@@ -821,3 +821,30 @@ def test_morton_key_source(rays_lib):
     cell = (np.clip(np.floor((s0[0] - x[0]) / (x[1] - x[0])), 0, 31) * 32 + np.clip(np.floor((s0[1] - x[0]) / (x[1] - x[0])), 0, 31))[order]
     changes = np.count_nonzero(np.diff(cell[2:]))                   # (skipping the two non-finite rays)
     assert changes < 2 * 1024                                       # ~1 change per occupied column, not per ray
+
+
+# ------------------------------------------------------------------------------------------- ElectronCube.dndr
+@pytest.mark.parametrize("par", [2, 1, 0])
+def test_dndr_lookup_source_matches_reference(dndr_lib, trace_lib, golden, par):
+    """ElectronCube.dndr / the dnd?_interp objects (particle_tracker.py:239-256) from the sources of calc_dndr and of
+    the look-up kernel: faces inclusive, exactly zero outside, against the live reference's RegularGridInterpolator
+    values on the 12 x 10 x 14 cube"""
+    g = golden("calc_dndr")
+    x = np.linspace(g["x"][0], g["x"][-1], 12)
+    y = np.linspace(g["y"][0], g["y"][-1], 10)
+    z = np.linspace(g["z"][0], g["z"][-1], 14)
+    _, G = _host_calc_dndr(dndr_lib, g["ne"], x, y, z, par, ne_max=float(g["ne_max"]), lwl=float(g["lwl"]))
+    pts = np.ascontiguousarray(g["pts"])
+    out = np.full_like(pts, np.nan)
+    vp = C.c_void_p
+    trace_lib.host_dndr.argtypes = [vp, C.c_int, C.POINTER(C.c_int * 3), C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 3),
+                                    C.c_int, vp, C.c_long, vp]
+    org = (C.c_double * 3)(x[0], y[0], z[0])
+    h = (C.c_double * 3)(*[(a[-1] - a[0]) / (len(a) - 1) for a in (x, y, z)])
+    p = lambda a: a.ctypes.data_as(vp)
+    assert trace_lib.host_dndr(p(G), 1, C.byref((C.c_int * 3)(12, 10, 14)), C.byref(org), C.byref(h), par, p(pts),
+                               pts.shape[1], p(out)) == 0
+    ref = g["dndr_at_pts"]
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+    outside = (np.abs(pts[0]) > x[-1]) | (pts[1] < y[0]) | (pts[1] > y[-1]) | (pts[2] < z[0]) | (pts[2] > z[-1])
+    assert outside.any() and np.all(out[:, outside] == 0)

@@ -61,36 +61,13 @@ __global__ void __launch_bounds__(128, sizeof(T) == 8 ? 2 : TT_TRACE_MIN_BLOCKS)
     }   // grid-stride loop
 }
 
-// ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at arbitrary points,
-// zero outside, faces inclusive (scipy _rgi.py:635-642).
+// ElectronCube.dndr (particle_tracker.py:243-256): one point per thread, the look-up itself in trace_gather_ray.cuh
 template <typename T>
 __global__ void dndr_kernel(const typename GridT<T>::V4* __restrict__ grid, TraceArgs A,
                             const double* __restrict__ pos, long npts, double* __restrict__ out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npts) return;
-    double g3[3] = {0.0, 0.0, 0.0};
-    double X[3];
-    bool inside = true;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double p = pos[(size_t)A.fa[k] * npts + i];
-        // inclusive faces tested on the physical coordinate, like the reference
-        const double hi = A.o[k] + A.h[k] * (A.n[k] - 1);
-        inside = inside && !(p < A.o[k]) && !(p > hi) && p == p;
-        X[k] = (p - A.o[k]) / A.h[k];
-    }
-    if (inside) {
-        int c[3]; T t[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double fl = floor(X[k]);
-            cell_of<T>((int)fl, (T)(X[k] - fl), A.n[k], c[k], t[k]);
-        }
-        G3<T> g = trilinear<T>(grid, A.n[0], (size_t)A.n[0] * A.n[1], c[0], c[1], c[2], t[0], t[1], t[2]);
-        g3[0] = (double)g.x; g3[1] = (double)g.y; g3[2] = (double)g.z;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) out[(size_t)A.fa[k] * npts + i] = g3[k] * (kC * kC);
+    dndr_point<T>(grid, A, pos, npts, i, out);
 }
 
 static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3],

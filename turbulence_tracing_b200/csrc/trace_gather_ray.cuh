@@ -382,4 +382,34 @@ TT_HD unsigned gather_ray(const typename GridT<T>::V4* __restrict__ grid, const 
     return steps;
 }
 
+// ElectronCube.dndr (particle_tracker.py:243-256): trilinear gradient at point i of pos[3][npts], zero outside,
+// faces inclusive (scipy _rgi.py:635-642); out[3][npts] in the reference's units (c^2 times the grid's 1/m)
+template <typename T>
+TT_HD void dndr_point(const typename GridT<T>::V4* __restrict__ grid, const TraceArgs& A, const double* __restrict__ pos,
+                      long npts, long i, double* __restrict__ out) {
+    double g3[3] = {0.0, 0.0, 0.0};
+    double X[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double p = pos[(size_t)A.fa[k] * npts + i];
+        // inclusive faces tested on the physical coordinate, like the reference
+        const double hi = A.o[k] + A.h[k] * (A.n[k] - 1);
+        inside = inside && !(p < A.o[k]) && !(p > hi) && p == p;
+        X[k] = (p - A.o[k]) / A.h[k];
+    }
+    if (inside) {
+        int c[3]; T t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double fl = floor(X[k]);
+            cell_of<T>((int)fl, (T)(X[k] - fl), A.n[k], c[k], t[k]);
+        }
+        G3<T> g = trilinear<T>(grid, A.n[0], (size_t)A.n[0] * A.n[1], c[0], c[1], c[2], t[0], t[1], t[2]);
+        g3[0] = (double)g.x; g3[1] = (double)g.y; g3[2] = (double)g.z;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[(size_t)A.fa[k] * npts + i] = g3[k] * (kC * kC);
+}
+
 }  // namespace tt
