@@ -9,7 +9,11 @@
  * Conventions
  *   - plain pointers and sizes only; every *_dev pointer is DEVICE memory owned by the caller,
  *     every other pointer is HOST memory.  The library allocates nothing persistent: scratch
- *     space is passed in after a *_workspace() size query.
+ *     space is passed in after a *_workspace() size query.  One exception, 4 bytes: tt_trace /
+ *     tt_trace_aux / tt_trace_axes take a stream-ordered flag word ("did the first pass defer a
+ *     ray?") from the device's default memory pool (cudaMallocAsync / cudaFreeAsync on `stream`)
+ *     and, on first use, set that pool's release threshold so that it keeps its memory across
+ *     synchronisations -- without it the allocation costs milliseconds per launch.
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); entry points that return
  *     device results do not synchronise.  The *_host convenience entry points (host buffers
  *     in and out) synchronise before returning.
