@@ -423,7 +423,7 @@ def run_gpu_arm(args, wl):
             e2e_events.append(marks)
             return H, cube2._steps_dev
 
-        ms2, tot2, _, _ = timed(step_e2e, cube2, 2, args.steps)
+        ms2, tot2, _, _ = timed(step_e2e, cube2, max(2, min(args.warmup, 3)), args.steps)
         e2e_names = ["h2d_cube+calc_dndr", "h2d_rays+sort+trace", "optics+hist+d2h"]
         e2e = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / args.steps,
                "phases_ms": {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in e2e_events[-args.steps:]]))
