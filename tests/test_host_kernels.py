@@ -848,3 +848,33 @@ def test_dndr_lookup_source_matches_reference(dndr_lib, trace_lib, golden, par):
     np.testing.assert_allclose(out, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
     outside = (np.abs(pts[0]) > x[-1]) | (pts[1] < y[0]) | (pts[1] > y[-1]) | (pts[2] < z[0]) | (pts[2] > z[-1])
     assert outside.any() and np.all(out[:, outside] == 0)
+
+
+def test_c2_size_sample_from_kernel_sources_on_the_host(dndr_lib, trace_lib, optics_lib):
+    """BASELINE configs[1] at its real size on the CPU: 257^3 k^-11/3 cube, 4096 rays of the configs' beam through the
+    sources of calc_dndr (FP32 in / FP32 out path, launch replayed), of the production trace kernel (1 step per cell) and
+    of the optics + histogram kernel, against the C oracle (one step sequence per ray at rtol 1e-13) on the same cube:
+    exit positions within 1e-3 pixel, shadowgraphy / dark-field / light-field images within L1 <= 1e-3"""
+    import bench
+    from oracle import ref_numpy as orc
+    from turbulence_tracing_b200 import ray_transfer_matrix as rtm
+    ne = bench.host_grf_cube(128, seed=3).astype(np.float32)            # float32 values, identical on both sides
+    x = np.linspace(-5e-3, 5e-3, 257)
+    np.random.seed(11)
+    s0 = orc.init_beam(4096, 4e-3, 0.05e-3, 5e-3, "z")
+    ref = orc_c.solve(orc_c.make_field(ne.astype(np.float64), x, x, x), s0, 5e-3, "z", rtol=1e-13, atol=1e-16, batch=1)[0]
+    _, G = _host_calc_dndr(dndr_lib, ne, x, x, x, 2, out_dtype=np.float32)
+    rf, sf, st, steps, nd = _run_trace(trace_lib, G, x, x, x, 2, 5e-3, s0, 1)
+    assert np.all(st == EXIT_FACE) and nd == 0 and steps == 256 * s0.shape[1]
+    p, a = _errors(rf, ref)
+    rms = np.sqrt(np.mean(ref[1] ** 2 + ref[3] ** 2))
+    print(f"257^3 on the host, fp32 1 step/cell vs C oracle: {p:.2e} m = {p / 52.3e-6:.1e} pixel, angle {a:.1e} of rms "
+          f"({rms * 1e3:.2f} mrad)")
+    assert p <= 1e-3 * 52.3e-6
+    for name, cls, skw in (("shadowgraphy", rtm.Shadowgraphy, {}), ("schlieren_df", rtm.Schlieren_DF, {"R": 1}),
+                           ("schlieren_lf", rtm.Schlieren_LF, {"R": 1})):
+        H = _host_optics(optics_lib, rf, _detector_program(cls, None, skw), hist=(18, 13.5, 344, 257))[1]
+        Href = orc.histogram(orc.detector(name, ref, **({"R_stop": 1} if skw else {})))[0]
+        l1 = np.abs(H.astype(np.float64) - Href).sum() / max(Href.sum(), 1)
+        print(f"   {name}: {int(H.sum())} rays binned, L1 distance to the oracle image {l1:.1e}")
+        assert l1 <= 1e-3
