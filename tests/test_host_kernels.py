@@ -878,3 +878,22 @@ def test_c2_size_sample_from_kernel_sources_on_the_host(dndr_lib, trace_lib, opt
         l1 = np.abs(H.astype(np.float64) - Href).sum() / max(Href.sum(), 1)
         print(f"   {name}: {int(H.sum())} rays binned, L1 distance to the oracle image {l1:.1e}")
         assert l1 <= 1e-3
+
+
+def test_rectilinear_body_on_uniform_axes_equals_uniform_body(host_lib, event_lib, golden):
+    """the two event-marching bodies are the same scheme: fed the same uniformly spaced axes they must agree to rounding
+    (FP64: the cell fraction comes from (x - x_i) / h instead of x / h - floor; FP32 grid: 1e-3 pixel bar)"""
+    g = golden("trace_grf33")
+    x, ne, s0 = g["x"], g["ne"], g["s0"]
+    for spc in (1, 4):
+        G = _grid4(ne, x, x, x, 2, np.float64)
+        r = _run(host_lib, G, x, x, x, 2, float(g["extent"]), s0, spc)
+        u = _run_uniform(event_lib, G, x, x, x, 2, float(g["extent"]), s0, spc)
+        np.testing.assert_array_equal(r[2], u[2])
+        assert r[3] == u[3] and r[4] == u[4] == 0
+        np.testing.assert_allclose(r[0], u[0], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r[1][:3], u[1][:3], rtol=0, atol=1e-12)
+        G32 = _grid4(ne, x, x, x, 2, np.float32)
+        r32 = _run(host_lib, G32, x, x, x, 2, float(g["extent"]), s0, spc)[0]
+        u32 = _run_uniform(event_lib, G32, x, x, x, 2, float(g["extent"]), s0, spc)[0]
+        assert np.abs(r32[0::2] - u32[0::2]).max() <= 1e-3 * 52.3e-6
