@@ -16,6 +16,11 @@ namespace tt {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+#ifndef TT_EVENT_LEAN
+#define TT_EVENT_LEAN 0            // (packed kernel) experiment prepared for round 2, NOT measured yet: the prefetch of plane
+                                   // k+2 issued where the cell changes instead of behind a flag at the loop top -- same
+                                   // loads, same results (host-tested bit-identical), a few control instructions less
+#endif
 // Returns the (sub-)plane arrivals of this ray (0 if it is deferred to the general kernel).
 template <typename T, bool SPC1>
 TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0, long ray,
@@ -338,6 +343,17 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
             }
         };
         load_cell();
+#if TT_EVENT_LEAN
+        // corners of plane k+2, loaded right after the cell changes instead of behind a flag test at the loop top
+        auto load_next = [&]() {
+            if (k + 2 <= nw - 1) {
+                const float4* p2 = p + 2 * plane;
+                n00 = GridT<float>::ld(p2); n10 = GridT<float>::ld(p2 + 1); n01 = GridT<float>::ld(p2 + nu); n11 = GridT<float>::ld(p2 + nu + 1);
+            }
+        };
+        load_next();
+        while (true) {
+#else
         bool have_next = false;
         while (true) {
             if (!have_next && k + 2 <= nw - 1) {
@@ -345,6 +361,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 n00 = GridT<float>::ld(p2); n10 = GridT<float>::ld(p2 + 1); n01 = GridT<float>::ld(p2 + nu); n11 = GridT<float>::ld(p2 + nu + 1);
                 have_next = true;
             }
+#endif
             // ---- stage 1 and the length of this step -------------------------------------------
             T q = trcp<T>(dw), hq = hw * q;
             bool ok = dw > T(TT_MARCH_MIN_DW);
@@ -479,7 +496,11 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                         tri2_advance(bxy, TT_XY(b00), TT_XY(b10), TT_XY(b01), TT_XY(b11));
                         tri2_advance(bzk, TT_ZW(b00), TT_ZW(b10), TT_ZW(b01), TT_ZW(b11));
                     }
+#if TT_EVENT_LEAN
+                    load_next();
+#else
                     have_next = false;
+#endif
                 }
             } else {
                 fw += h;
@@ -492,7 +513,11 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 tuv = pk2(tu, tv);
                 if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
                 load_cell();
+#if TT_EVENT_LEAN
+                load_next();
+#else
                 have_next = false;
+#endif
             }
         }
     }
