@@ -38,6 +38,11 @@ TT_HD int find_cell(const double* __restrict__ ax, int n, double x) {
 // the FP64 gather kernel of trace_axes.cu stays the second pass for everything unusual (launched outside the cube beside
 // the entry face, steep / backward, side exit, possible time cap, non-finite): those rays are flagged
 // TT_RAY_DEFERRED and redone from s0.
+#ifndef TT_AXES_RCP
+#define TT_AXES_RCP 0              // experiment prepared for round 2, NOT measured yet: keep 1/h_u, 1/h_v of the current cell
+                                   // (refreshed at u / v crossings only) so that a plane arrival costs two multiplications
+                                   // instead of two divisions (the FP32 kernel has the XU pipe at 18 %); host-tested
+#endif
 // Returns the (sub-)plane arrivals of this ray (0 if deferred).
 template <typename T>
 TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0, long ray,
@@ -81,7 +86,12 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
         }
     }
     R du = D[0], dv = D[1], dw = D[2], s = 0;
+#if TT_AXES_RCP
+    R ihu = R(1) / hu, ihv = R(1) / hv;
+    R ru = hw * ihu, rv = hw * ihv;
+#else
     R ru = hw / hu, rv = hw / hv;
+#endif
     const int spc = A.spc;
     const R hsub = R(1) / (R)spc;
     int j = (int)(fw * (R)spc);               // current sub-plane interval of the w-cell
@@ -160,7 +170,11 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
                     if (++k >= nw - 1) break;                                 // far face: done
                     p += plane;
                     hw = ldg_f64(axw + k + 1) - ldg_f64(axw + k);
+#if TT_AXES_RCP
+                    ru = hw * ihu; rv = hw * ihv;
+#else
                     ru = hw / hu; rv = hw / hv;
+#endif
                     load_cell();
                 }
             } else {
@@ -174,12 +188,22 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
                     xu0 = ldg_f64(axu + cu);
                     const R hn = ldg_f64(axu + cu + 1) - xu0, sc = hu / hn;
                     tu = cross == 1 ? (tu - R(1)) * sc : fma(tu, sc, R(1));
-                    hu = hn; ru = hw / hu;
+                    hu = hn;
+#if TT_AXES_RCP
+                    ihu = R(1) / hu; ru = hw * ihu;
+#else
+                    ru = hw / hu;
+#endif
                 } else {
                     xv0 = ldg_f64(axv + cv);
                     const R hn = ldg_f64(axv + cv + 1) - xv0, sc = hv / hn;
                     tv = cross == 2 ? (tv - R(1)) * sc : fma(tv, sc, R(1));
-                    hv = hn; rv = hw / hv;
+                    hv = hn;
+#if TT_AXES_RCP
+                    ihv = R(1) / hv; rv = hw * ihv;
+#else
+                    rv = hw / hv;
+#endif
                 }
                 load_cell();
             }
