@@ -23,6 +23,9 @@ namespace tt {
 #ifndef TT_EVENT_MIN_BLOCKS
 #define TT_EVENT_MIN_BLOCKS 5        // FP32: 95 registers, no spills -> 20 warps / SM
 #endif
+#ifndef TT_EVENT_BLOCK
+#define TT_EVENT_BLOCK 128           // threads per CTA of the packed kernel (A/B: 64 with TT_EVENT_MIN_BLOCKS=10, 256 with 2)
+#endif
 #ifndef TT_EVENT_MIN_BLOCKS_AUX
 #define TT_EVENT_MIN_BLOCKS_AUX 3    // passive quantities on board: four packed polynomials, 168 registers
 #endif
@@ -64,7 +67,7 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
 
 // CUBIC: h_u = h_v = h_w, so the index-space slopes need no rescaling (x * 1.0f is exact: same bits).
 template <bool SPC1, bool AUX, bool CUBIC>
-__global__ void __launch_bounds__(128, AUX ? TT_EVENT_MIN_BLOCKS_AUX : TT_EVENT_MIN_BLOCKS)
+__global__ void __launch_bounds__(TT_EVENT_BLOCK, AUX ? TT_EVENT_MIN_BLOCKS_AUX : TT_EVENT_MIN_BLOCKS)
 trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
                          const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
                          unsigned long long* __restrict__ ray_steps, uint8_t* __restrict__ status, TraceArgs A,
@@ -90,8 +93,10 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
 int launch_trace_event(int dtype, bool packed, int steps_per_cell, const void* grid4, const double* s0,
                        const uint32_t* perm, double* rf, double* sf, unsigned long long* ray_steps, uint8_t* status,
                        const TraceArgs& A, const void* aux4, double* aux_out, const AuxArgs& AX, cudaStream_t s) {
-    const int block = 128;
+    const int block = TT_EVENT_BLOCK;      // packed kernel
     const unsigned blocks = (unsigned)((A.np + block - 1) / block);
+    const int block_s = 128;               // scalar kernels (their launch bounds)
+    const unsigned blocks_s = (unsigned)((A.np + block_s - 1) / block_s);
     const bool spc1 = steps_per_cell == 1;
     const bool cubic = A.ruf == 1.0f && A.rvf == 1.0f;
 #define TT_EV2(S1, AX_, CU, ...) trace_event_kernel_f32x2<S1, AX_, CU><<<blocks, block, 0, s>>>(__VA_ARGS__)
@@ -111,11 +116,11 @@ int launch_trace_event(int dtype, bool packed, int steps_per_cell, const void* g
 #undef TT_EV2_DISPATCH
 #undef TT_EV2
     if (dtype == TT_F32) {
-        if (spc1) trace_event_kernel<float, true><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
-        else trace_event_kernel<float, false><<<blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
+        if (spc1) trace_event_kernel<float, true><<<blocks_s, block_s, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
+        else trace_event_kernel<float, false><<<blocks_s, block_s, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
     } else {
-        if (spc1) trace_event_kernel<double, true><<<blocks, block, 0, s>>>((const double4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
-        else trace_event_kernel<double, false><<<blocks, block, 0, s>>>((const double4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
+        if (spc1) trace_event_kernel<double, true><<<blocks_s, block_s, 0, s>>>((const double4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
+        else trace_event_kernel<double, false><<<blocks_s, block_s, 0, s>>>((const double4*)grid4, s0, perm, rf, sf, ray_steps, status, A);
     }
     return launch_check("trace_event_kernel");
 }
