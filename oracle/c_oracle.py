@@ -33,8 +33,9 @@ class _Field(C.Structure):
 def build(force=False):
     """gcc the restatement (oracle/Makefile); a no-op when the library is newer than its source."""
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
-        subprocess.run(["make", "-s", "-C", HERE] + (["-B"] if force else []), check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        r = subprocess.run(["make", "-s", "-C", HERE] + (["-B"] if force else []), capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(LIB):
+            raise RuntimeError("building oracle/tt_oracle.c failed:\n" + r.stdout + r.stderr)
     return LIB
 
 
