@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Builds A/B variants of libtt_b200.so that differ only in trace_event.cu (the production trace kernel):
+
+    python scripts/build_variants.py            # -> build/variants/libtt_b200_<tag>.so (travels to the GPU box)
+
+Every other object is reused from build/obj (run `python -m turbulence_tracing_b200.build` first).  `r1` compiles the
+kernel headers of the commit given by TT_R1_COMMIT (default: the round-1 head) as the baseline.
+Select a variant at run time with TT_B200_LIB=<path> (turbulence_tracing_b200/_lib.py)."""
+import os, shutil, subprocess, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from turbulence_tracing_b200 import build as B
+
+VARIANTS = {
+    "new": [],
+    "nomerge": ["-DTT_EVENT_MERGE=0"],
+    "nofastdiv": ["-DTT_EVENT_FASTDIV=0"],
+    "lean": ["-DTT_EVENT_LEAN=1"],
+    "b64": ["-DTT_EVENT_BLOCK=64", "-DTT_EVENT_MIN_BLOCKS=10"],
+    "b256": ["-DTT_EVENT_BLOCK=256", "-DTT_EVENT_MIN_BLOCKS=2"],
+    "mb6": ["-DTT_EVENT_MIN_BLOCKS=6"],
+    "mb4": ["-DTT_EVENT_MIN_BLOCKS=4"],
+    "b96": ["-DTT_EVENT_BLOCK=96", "-DTT_EVENT_MIN_BLOCKS=7"],      # 21 warps / SM at 96 registers
+}
+R1 = os.environ.get("TT_R1_COMMIT", "73762f2")
+
+
+def main():
+    only = sys.argv[1:]
+    B.build()
+    out = os.path.join(ROOT, "build", "variants")
+    os.makedirs(out, exist_ok=True)
+    nvcc = B._nvcc()
+    objs = [os.path.join(B.OBJ, s[:-3] + ".o") for s in B.SOURCES if s != "trace_event.cu"]
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+
+    def link(tag, obj):
+        lib = os.path.join(out, f"libtt_b200_{tag}.so")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, obj, *objs, "-L" + cuda_lib,
+                        "-lcufft", "-Xlinker", "-rpath," + cuda_lib], check=True)
+        print(lib)
+
+    for tag, flags in VARIANTS.items():
+        if only and tag not in only:
+            continue
+        obj = os.path.join(out, f"trace_event_{tag}.o")
+        subprocess.run([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B.CSRC, "trace_event.cu"), "-o", obj], check=True)
+        link(tag, obj)
+    if not only or "r1" in only:
+        # the round-1 kernel: csrc of that commit, compiled against the current ABI header
+        with tempfile.TemporaryDirectory() as tmp:
+            subprocess.run(f"git -C {ROOT} archive {R1} turbulence_tracing_b200/csrc | tar -x -C {tmp}", shell=True, check=True)
+            csrc = os.path.join(tmp, "turbulence_tracing_b200", "csrc")
+            flags = [f for f in B.NVCC_FLAGS if not f.startswith("-I" + B.CSRC)] + ["-I" + csrc]
+            obj = os.path.join(out, "trace_event_r1.o")
+            subprocess.run([nvcc, *flags, "-c", os.path.join(csrc, "trace_event.cu"), "-o", obj], check=True)
+            link("r1", obj)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libtt_b200.so")
+# TT_B200_LIB: another build of the same library (A/B runs of kernel variants, scripts/build_variants.py)
+LIB_PATH = os.environ.get("TT_B200_LIB") or os.path.join(PKG, "libtt_b200.so")
 
 TT_F32, TT_F64 = 0, 1
 TT_OK = 0

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <mutex>
+
 namespace tt {
 
 static thread_local char g_err[512] = "";
@@ -14,20 +16,41 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Stream-ordered 4-byte scratch word ("did the event kernel defer any ray?").  It comes from a memory pool OWNED BY
+// THIS LIBRARY (one per device, created on first use, release threshold = keep): cudaMallocAsync from the device's
+// default pool right after a synchronisation costs 0.7-15 ms on a B200 VM (the pool hands its memory back to the
+// driver at every sync, profiles/r01_diag_mallocasync.txt), and changing the default pool's threshold would change
+// the behaviour of every other cudaMallocAsync user in the host process.
 unsigned int* scratch_flag(cudaStream_t s) {
-    static bool pool_kept[64] = {};             // per device; a benign race sets the same attribute twice
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    static bool tried[64] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_kept[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!tried[dev]) {
+            tried[dev] = true;
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t made = nullptr;
+            if (cudaMemPoolCreate(&made, &props) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(made, cudaMemPoolAttrReleaseThreshold, &keep);
+                pools[dev] = made;
+            }
+            (void)cudaGetLastError();
         }
-        (void)cudaGetLastError();
-        pool_kept[dev] = true;
+        pool = pools[dev];
     }
     unsigned int* flag = nullptr;
-    if (cudaMallocAsync((void**)&flag, sizeof(unsigned int), s) != cudaSuccess) {
+    const cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&flag, sizeof(unsigned int), pool, s)
+                               : cudaMallocAsync((void**)&flag, sizeof(unsigned int), s);
+    if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return nullptr;
     }

@@ -126,7 +126,7 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
         // event marching (packed FP32x2 arithmetic for variant 3 in FP32), then the second pass below
         int rc2 = launch_trace_event(p->dtype, variant == 3, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, nullptr, nullptr, AuxArgs(), s);
-        if (rc2) return rc2;
+        if (rc2) { if (flag) cudaFreeAsync(flag, s); return rc2; }
         only_flagged = 1;          // second pass: the general kernel on the deferred rays only
         variant = 2;
     }
@@ -174,7 +174,7 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
         // event marching with the passive quantities on board; the gather kernel then redoes the deferred rays
         int rc2 = launch_trace_event(TT_F32, true, p->steps_per_cell, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev,
                                      ray_steps_dev, status_dev, A, aux4_dev, aux_out_dev, AX, s);
-        if (rc2) return rc2;
+        if (rc2) { if (flag) cudaFreeAsync(flag, s); return rc2; }
         only_flagged = 1;
     }
     const long blocks2 = only_flagged && blocks > 148 * 32 ? 148 * 32 : blocks;

@@ -135,6 +135,22 @@ TT_HD void tri_advance(Tri<T>& q, T n00, T n10, T n01, T n11) {
     q.a1 = n00 - q.a; q.b1 = eb - q.b; q.c1 = (n01 - n00) - q.c; q.d1 = ((n11 - n01) - eb) - q.d;
 }
 
+// the two halves of tri_set / tri_advance (same operations on the same operands): base plane from its 4 corners or by
+// stepping one plane, then the primed half from the 4 corners of the far plane
+template <typename T>
+TT_HD void tri_base(Tri<T>& q, T c00, T c10, T c01, T c11) {
+    q.a = c00; q.b = c10 - c00; q.c = c01 - c00; q.d = (c11 - c01) - q.b;
+}
+template <typename T>
+TT_HD void tri_base_step(Tri<T>& q) {
+    q.a += q.a1; q.b += q.b1; q.c += q.c1; q.d += q.d1;
+}
+template <typename T>
+TT_HD void tri_primed(Tri<T>& q, T n00, T n10, T n01, T n11) {
+    T eb = n10 - n00;
+    q.a1 = n00 - q.a; q.b1 = eb - q.b; q.c1 = (n01 - n00) - q.c; q.d1 = ((n11 - n01) - eb) - q.d;
+}
+
 template <typename T>
 struct Ray {
     int iu, iv, iw;

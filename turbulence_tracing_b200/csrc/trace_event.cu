@@ -66,7 +66,8 @@ trace_event_kernel(const typename GridT<T>::V4* __restrict__ grid, const double*
 // (f32x2 helpers, Tri2 / Bil2 and the per-ray body event_ray_f32x2 live in trace_event_ray.cuh: host + device)
 
 // CUBIC: h_u = h_v = h_w, so the index-space slopes need no rescaling (x * 1.0f is exact: same bits).
-template <bool SPC1, bool AUX, bool CUBIC>
+// TRACK_S: sf (state at time T) wanted -> the path time is accumulated; false drops that bookkeeping from the loop.
+template <bool SPC1, bool AUX, bool CUBIC, bool TRACK_S>
 __global__ void __launch_bounds__(TT_EVENT_BLOCK, AUX ? TT_EVENT_MIN_BLOCKS_AUX : TT_EVENT_MIN_BLOCKS)
 trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0,
                          const uint32_t* __restrict__ perm, double* __restrict__ rf, double* __restrict__ sf,
@@ -78,7 +79,7 @@ trace_event_kernel_f32x2(const float4* __restrict__ grid, const double* __restri
     if (tid < A.np) {
         const long ray = perm ? (long)perm[tid] : tid;
         bool deferred = false;
-        steps = event_ray_f32x2<SPC1, AUX, CUBIC>(grid, s0, ray, rf, sf, status, A, aux4, aux_out, AX, deferred);
+        steps = event_ray_f32x2<SPC1, AUX, CUBIC, TRACK_S>(grid, s0, ray, rf, sf, status, A, aux4, aux_out, AX, deferred);
         if (deferred && A.any_deferred) *A.any_deferred = 1u;       // (benign race: everybody stores 1)
     }
     if (ray_steps) {
@@ -99,7 +100,11 @@ int launch_trace_event(int dtype, bool packed, int steps_per_cell, const void* g
     const unsigned blocks_s = (unsigned)((A.np + block_s - 1) / block_s);
     const bool spc1 = steps_per_cell == 1;
     const bool cubic = A.ruf == 1.0f && A.rvf == 1.0f;
-#define TT_EV2(S1, AX_, CU, ...) trace_event_kernel_f32x2<S1, AX_, CU><<<blocks, block, 0, s>>>(__VA_ARGS__)
+#define TT_EV2(S1, AX_, CU, ...)                                                                          \
+    do {                                                                                                  \
+        if (AX_ || sf) trace_event_kernel_f32x2<S1, AX_, CU, true><<<blocks, block, 0, s>>>(__VA_ARGS__);  \
+        else trace_event_kernel_f32x2<S1, AX_, CU, AX_><<<blocks, block, 0, s>>>(__VA_ARGS__);             \
+    } while (0)
 #define TT_EV2_DISPATCH(AX_, ...)                                                       \
     do {                                                                                \
         if (spc1) { if (cubic) TT_EV2(true, AX_, true, __VA_ARGS__); else TT_EV2(true, AX_, false, __VA_ARGS__); }   \

@@ -21,6 +21,28 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
                                    // k+2 issued where the cell changes instead of behind a flag at the loop top -- same
                                    // loads, same results (host-tested bit-identical), a few control instructions less
 #endif
+#ifndef TT_EVENT_MERGE
+#define TT_EVENT_MERGE 1           // a cell change (next plane OR a u / v face) renews the polynomial in two halves: the base
+                                   // plane (advance: base += primed; face: 4 corners of the new column) and, in code COMMON
+                                   // to both, the primed half from the 4 corners of the far plane.  Same operations on the
+                                   // same operands as tri_set / tri_advance (bit-identical rays), but the part of the
+                                   // relabelling that a warp executes for one or two lanes only shrinks by ~50 instructions
+#endif
+#ifndef TT_EVENT_FASTDIV
+#define TT_EVENT_FASTDIV 1         // chord fractions of a predicted face crossing with MUFU.RCP instead of IEEE divisions
+                                   // (they only decide where the step is split; the ray keeps its true position)
+#endif
+// chord fraction num / den of a predicted face crossing (den != 0); NaN (0 * inf) and overflow -> 2 = "not reached"
+template <typename T>
+TT_HD T chord_fraction(T num, T den) {
+#if TT_EVENT_FASTDIV
+    const T l = num * trcp<T>(den);
+    return l < T(2) ? l : T(2);                 // false for NaN
+#else
+    return num / den;
+#endif
+}
+
 // Returns the (sub-)plane arrivals of this ray (0 if it is deferred to the general kernel).
 template <typename T, bool SPC1>
 TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0, long ray,
@@ -99,8 +121,8 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
                     // fraction of the remaining interval at which the chord reaches the face the ray
                     // is heading for (a zero slope never reaches a face)
                     T lu = T(2), lv = T(2);
-                    if (aU > T(0)) lu = (T(1) - tu) / (h * aU); else if (aU < T(0)) lu = -tu / (h * aU);
-                    if (aV > T(0)) lv = (T(1) - tv) / (h * aV); else if (aV < T(0)) lv = -tv / (h * aV);
+                    if (aU > T(0)) lu = chord_fraction<T>(T(1) - tu, h * aU); else if (aU < T(0)) lu = chord_fraction<T>(-tu, h * aU);
+                    if (aV > T(0)) lv = chord_fraction<T>(T(1) - tv, h * aV); else if (aV < T(0)) lv = chord_fraction<T>(-tv, h * aV);
                     T lam = fmin(lu, lv);
                     if (lam < T(1)) {
                         cross = lu <= lv ? (aU > T(0) ? 1 : -1) : (aV > T(0) ? 2 : -2);
@@ -137,6 +159,40 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
             dw = tfma(h6, adw + T(2) * (bdw + cdw) + edw, dw);
             if (track_s) s = tfma(h6, as + T(2) * (bs + cs) + es, s);
             if (!(ok && dw > T(TT_MARCH_MIN_DW))) { fast = false; break; }   // steep / turning / NaN
+#if TT_EVENT_MERGE
+            bool renew = true;
+            if (cross == 0) {
+                // ---- reached the next (sub-)plane: plane k+1 becomes the base plane -----------
+                ++steps;
+                fw = fw_t;
+                if (SPC1 || ++j == spc) {
+                    j = 0; fw = T(0);
+                    if (++k >= nw - 1) break;                                     // far face: done
+                    p += plane;
+                    tri_base_step<T>(qx); tri_base_step<T>(qy); tri_base_step<T>(qz);
+                } else {
+                    renew = false;
+                }
+            } else {
+                // ---- reached a u / v cell face inside the w-cell: relabel, base plane of the new column ----
+                fw += h;
+                if (cross == 1) { ++cu; tu -= T(1); p += 1; } else if (cross == -1) { --cu; tu += T(1); p -= 1; }
+                else if (cross == 2) { ++cv; tv -= T(1); p += nu; } else { --cv; tv += T(1); p -= nu; }
+                if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }   // side exit
+                const V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+                tri_base<T>(qx, c00.x, c10.x, c01.x, c11.x);
+                tri_base<T>(qy, c00.y, c10.y, c01.y, c11.y);
+                tri_base<T>(qz, c00.z, c10.z, c01.z, c11.z);
+                const V4* p1 = p + plane;                                         // its far plane, into the prefetch registers
+                n00 = GridT<T>::ld(p1); n10 = GridT<T>::ld(p1 + 1); n01 = GridT<T>::ld(p1 + nu); n11 = GridT<T>::ld(p1 + nu + 1);
+            }
+            if (SPC1 || renew) {                  // common to both: the primed half from the 4 corners of the far plane
+                tri_primed<T>(qx, n00.x, n10.x, n01.x, n11.x);
+                tri_primed<T>(qy, n00.y, n10.y, n01.y, n11.y);
+                tri_primed<T>(qz, n00.z, n10.z, n01.z, n11.z);
+                have_next = false;
+            }
+#else
             if (cross == 0) {
                 // ---- reached the next (sub-)plane ---------------------------------------------
                 ++steps;
@@ -172,6 +228,7 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
                 tri_set<T>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
                 have_next = false;
             }
+#endif
         }
     }
     if (!fast) {
@@ -252,6 +309,18 @@ TT_HD void tri2_advance(Tri2& q, f32x2 n00, f32x2 n10, f32x2 n01, f32x2 n11) {
     q.a1 = sub2(n00, q.a); q.b1 = sub2(eb, q.b); q.c1 = sub2(sub2(n01, n00), q.c);
     q.d1 = sub2(sub2(sub2(n11, n01), eb), q.d);
 }
+// the two halves of tri2_set / tri2_advance (TT_EVENT_MERGE): same operations on the same operands
+TT_HD void tri2_base(Tri2& q, f32x2 c00, f32x2 c10, f32x2 c01, f32x2 c11) {
+    q.a = c00; q.b = sub2(c10, c00); q.c = sub2(c01, c00); q.d = sub2(sub2(c11, c01), q.b);
+}
+TT_HD void tri2_base_step(Tri2& q) {
+    q.a = add2(q.a, q.a1); q.b = add2(q.b, q.b1); q.c = add2(q.c, q.c1); q.d = add2(q.d, q.d1);
+}
+TT_HD void tri2_primed(Tri2& q, f32x2 n00, f32x2 n10, f32x2 n01, f32x2 n11) {
+    f32x2 eb = sub2(n10, n00);
+    q.a1 = sub2(n00, q.a); q.b1 = sub2(eb, q.b); q.c1 = sub2(sub2(n01, n00), q.c);
+    q.d1 = sub2(sub2(sub2(n11, n01), eb), q.d);
+}
 #define TT_XY(v) pk2((v).x, (v).y)
 #define TT_ZW(v) pk2((v).z, (v).w)
 
@@ -271,7 +340,8 @@ TT_HD void aux_integrands(float nn, f32x2 bxy, f32x2 bzk, f32x2 duv, float dw, f
 }
 
 // Returns the (sub-)plane arrivals of this ray (0 if it is deferred to the general kernel).
-template <bool SPC1, bool AUX, bool CUBIC>
+// TRACK_S = false: the caller passes sf == nullptr (no state at time T wanted), so the path time needs no bookkeeping
+template <bool SPC1, bool AUX, bool CUBIC, bool TRACK_S = true>
 TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __restrict__ s0, long ray,
                                double* __restrict__ rf, double* __restrict__ sf, uint8_t* __restrict__ status,
                                const TraceArgs& A, const float4* __restrict__ aux4, double* __restrict__ aux_out,
@@ -311,7 +381,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
     T dw = (T)D[2], s = 0.f;
     const T hw = A.hwf;
     const f32x2 RUV = pk2(A.ruf, A.rvf);
-    const bool track_s = sf != nullptr;
+    const bool track_s = TRACK_S && sf != nullptr;
     const int spc = A.spc;
     const T hsub = SPC1 ? 1.f : 1.f / (T)spc;
     int j = SPC1 ? 0 : (int)(fw * (T)spc);
@@ -391,8 +461,8 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                     const T aU = lo2(aUV), aV = hi2(aUV), tu = lo2(tuv), tv = hi2(tuv);
                     // (a branch-free variant with approximate divisions was measured slower: 459.6 vs 451.4 ms)
                     T lu = 2.f, lv = 2.f;
-                    if (aU > 0.f) lu = (1.f - tu) / (h * aU); else if (aU < 0.f) lu = -tu / (h * aU);
-                    if (aV > 0.f) lv = (1.f - tv) / (h * aV); else if (aV < 0.f) lv = -tv / (h * aV);
+                    if (aU > 0.f) lu = chord_fraction<T>(1.f - tu, h * aU); else if (aU < 0.f) lu = chord_fraction<T>(-tu, h * aU);
+                    if (aV > 0.f) lv = chord_fraction<T>(1.f - tv, h * aV); else if (aV < 0.f) lv = chord_fraction<T>(-tv, h * aV);
                     T lam = fminf(lu, lv);
                     if (lam < 1.f) {
                         cross = lu <= lv ? (aU > 0.f ? 1 : -1) : (aV > 0.f ? 2 : -2);
@@ -473,6 +543,62 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 }
             }
             if (!(ok && dw > T(TT_MARCH_MIN_DW))) { fast = false; break; }
+#if TT_EVENT_MERGE
+            bool renew = true;
+            if (cross == 0) {
+                ++steps;
+                fw = fw_t;
+                if (SPC1 || ++j == spc) {
+                    j = 0; fw = 0.f;
+                    if (++k >= nw - 1) break;
+                    p += plane;
+                    tri2_base_step(qxy);                              // plane k+1 becomes the base plane
+                    if (AUX) tri2_base_step(qzw); else tri_base_step<float>(qz);
+                    if (has_b) { pa += plane; tri2_base_step(bxy); tri2_base_step(bzk); }
+                } else {
+                    renew = false;
+                }
+            } else {
+                fw += h;
+                T tu = lo2(tuv), tv = hi2(tuv);
+                int dp = 0;
+                if (cross == 1) { ++cu; tu -= 1.f; dp = 1; } else if (cross == -1) { --cu; tu += 1.f; dp = -1; }
+                else if (cross == 2) { ++cv; tv -= 1.f; dp = nu; } else { --cv; tv += 1.f; dp = -nu; }
+                p += dp;
+                tuv = pk2(tu, tv);
+                if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
+                {                                                     // base plane of the new cell column
+                    const float4 c00 = GridT<float>::ld(p), c10 = GridT<float>::ld(p + 1), c01 = GridT<float>::ld(p + nu), c11 = GridT<float>::ld(p + nu + 1);
+                    tri2_base(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11));
+                    if (AUX) tri2_base(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11));
+                    else tri_base<float>(qz, c00.z, c10.z, c01.z, c11.z);
+                }
+                if (has_b) {
+                    pa += dp;
+                    const float4 c00 = GridT<float>::ld(pa), c10 = GridT<float>::ld(pa + 1), c01 = GridT<float>::ld(pa + nu), c11 = GridT<float>::ld(pa + nu + 1);
+                    tri2_base(bxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11));
+                    tri2_base(bzk, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11));
+                }
+                const float4* p1 = p + plane;                         // its far plane, into the prefetch registers
+                n00 = GridT<float>::ld(p1); n10 = GridT<float>::ld(p1 + 1); n01 = GridT<float>::ld(p1 + nu); n11 = GridT<float>::ld(p1 + nu + 1);
+            }
+            if (SPC1 || renew) {                                      // common to both: the primed half from the far plane
+                tri2_primed(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
+                if (AUX) tri2_primed(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
+                else tri_primed<float>(qz, n00.z, n10.z, n01.z, n11.z);
+                if (has_b) {
+                    const float4* q1 = pa + plane;
+                    const float4 b00 = GridT<float>::ld(q1), b10 = GridT<float>::ld(q1 + 1), b01 = GridT<float>::ld(q1 + nu), b11 = GridT<float>::ld(q1 + nu + 1);
+                    tri2_primed(bxy, TT_XY(b00), TT_XY(b10), TT_XY(b01), TT_XY(b11));
+                    tri2_primed(bzk, TT_ZW(b00), TT_ZW(b10), TT_ZW(b01), TT_ZW(b11));
+                }
+#if TT_EVENT_LEAN
+                load_next();
+#else
+                have_next = false;
+#endif
+            }
+#else
             if (cross == 0) {
                 ++steps;
                 fw = fw_t;
@@ -519,6 +645,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 have_next = false;
 #endif
             }
+#endif
         }
     }
     if (!fast) {
@@ -535,7 +662,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
         rf[1 * A.np + ray] = atan(Vu / Vw);
         rf[2 * A.np + ray] = Pv - Vv * tb;
         rf[3 * A.np + ray] = atan(Vv / Vw);
-        if (sf) {
+        if (TRACK_S && sf) {
             const double t_rest = (A.s_max - s_pre - (double)s) / kC;
             const double Pf[3] = {Pu, Pv, Pw}, Vf[3] = {Vu, Vv, Vw};
 #pragma unroll

@@ -531,8 +531,8 @@ class ElectronCube:
                     sf[:, lo:lo + n] = sf_c
                 if aux_out is not None:
                     aux_out[:, lo:lo + n] = ax_c
-                if perm is not None:
-                    perm[lo:lo + n] = pc + lo              # global ray ids, chunk after chunk
+                if perm is not None:                       # global ray ids, chunk after chunk (a 1-ray chunk is not sorted)
+                    perm[lo:lo + n] = (pc + lo) if pc is not None else torch.arange(lo, lo + n, dtype=torch.int32, device="cuda")
                 free[b] = torch.cuda.Event()
                 free[b].record(main)
                 if growth is None:                         # after the first chunk: pick the schedule
@@ -605,6 +605,9 @@ class ElectronCube:
     def ray_at_exit(self):
         """rf from ``self.sf`` by linear back-projection to the plane axis = +extent (:333-380)."""
         torch = _lib.torch_cuda()
+        if getattr(self, "sf", None) is None:
+            raise AttributeError("sf was not kept: construct the cube with keep_sf=True (the default) and call solve() first; "
+                                 "solve() already returns rf = ray_at_exit()")
         sf = _lib.to_device(self.sf, torch.float64)
         par = self._par
         t1, t2 = {2: (0, 1), 1: (0, 2), 0: (1, 2)}[par]

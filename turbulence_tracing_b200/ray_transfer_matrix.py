@@ -247,7 +247,13 @@ class Rays:
         # permuted gather costs a 128-byte DRAM transaction per 8-byte element: measured on B200 with
         # 1e8 rays, 7.8 ms against 2.3 ms for the streaming order.  Opt in with ``use_ray_order(perm)``.
         self._perm = None
-        self._r0_m = _lib.to_device(r0, torch.float64)      # metres; m_to_mm happens in the kernel
+        # the reference copies at construction (self.r0 = m_to_mm(r0), :172): a device input is cloned so that later
+        # in-place edits of the caller's array (e.g. cube.rf) cannot change this detector's image (32 B/ray, ~1 ms
+        # for 1e8 rays); host inputs are copied by the upload anyway
+        t = _lib.to_device(r0, torch.float64)
+        if isinstance(r0, (DeviceArray, torch.Tensor)) and t.data_ptr() == (r0.torch if isinstance(r0, DeviceArray) else r0).data_ptr():
+            t = t.clone()
+        self._r0_m = t                                      # metres; m_to_mm happens in the kernel
         self._r0_mm = None
         self._program = None
         self._rf = None
