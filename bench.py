@@ -133,11 +133,23 @@ _CPU = {}
 
 
 def _cpu_worker(args):
-    """One Pool worker = one bundle, as example_multiprocess.py:41-51: seed, init_beam, solve (scipy
-    RK45, default tolerances), shadowgraphy histogram."""
-    from oracle import ref_numpy as orc
+    """One Pool worker = one bundle, as example_multiprocess.py:41-51: seed, init_beam, solve (scipy RK45, default
+    tolerances), shadowgraphy histogram.  kind "reference": the reference's OWN ElectronCube / Shadowgraphy objects
+    (oracle/_ref, unmodified modules); kind "port": the numpy/scipy restatement (oracle/ref_numpy.py)."""
     i, n = args
     np.random.seed(1000 + i)
+    if _CPU["kind"] == "reference":
+        from oracle import reference_live as live
+        pt, rtm, _ = live.load()
+        cube = _CPU["cube"]
+        cube.init_beam(n, BEAM_SIZE, DIVERGENCE)
+        with live.NfevCounter(pt) as cnt:
+            rf = live.quiet(cube.solve)
+        sh = rtm.Shadowgraphy(rf)
+        sh.solve()
+        sh.histogram(bin_scale=10)
+        return n, cnt.nfev * n, sh.H.sum()
+    from oracle import ref_numpy as orc
     s0 = orc.init_beam(n, BEAM_SIZE, DIVERGENCE, EXTENT, "z")
     rf, sf, nfev = orc.solve(_CPU["field"], s0, EXTENT, "z")
     H, _, _ = orc.histogram(orc.detector("shadowgraphy", rf))
@@ -162,10 +174,23 @@ def host_grf_cube(n_half, seed=7):
     return ne_from_field(f.astype(np.float64), np)
 
 
-def cpu_reference_setup(ne_host, M):
-    from oracle import ref_numpy as orc
+def cpu_reference_setup(ne_host, M, prefer_reference=True):
+    """The CPU arm's field: the reference's own ElectronCube (external_ne + calc_dndr, particle_tracker.py:212-241) when
+    its modules are at hand (oracle/_ref on the GPU box, /root/reference in the build container), else the port.
+    The C restatement borrows the gradient arrays of whichever was built (no copy)."""
+    from oracle import reference_live as live
     x = np.linspace(-EXTENT, EXTENT, M)
-    _CPU["field"] = orc.make_field(ne_host, x, x, x, LWL)
+    if prefer_reference and live.available():
+        pt, _, where = live.load()
+        cube = pt.ElectronCube(x, x, x, "z")
+        cube.external_ne(ne_host)
+        cube.calc_dndr(LWL)
+        cube.ne = cube.ne_nc = None              # only the interpolators are used from here on
+        _CPU.update(kind="reference", cube=cube, where=where, grid=(x, x, x), grads=(cube.dndx, cube.dndy, cube.dndz))
+    else:
+        from oracle import ref_numpy as orc
+        f = orc.make_field(ne_host, x, x, x, LWL)
+        _CPU.update(kind="port", field=f, where="oracle/ref_numpy.py", grid=f.ix.grid, grads=(f.ix.values, f.iy.values, f.iz.values))
 
 
 def cpu_reference_step(rays_per_worker, cores, min_seconds=10.0, max_rounds=6):
@@ -196,9 +221,8 @@ def cpu_c_port_sample(cores, rays_per_bundle, min_seconds=3.0, max_rounds=40):
     the stronger CPU baseline; the gradient arrays are shared with the scipy field (no copy)."""
     from oracle import c_oracle as orc_c
     from oracle import ref_numpy as orc
-    f = _CPU["field"]
-    x, y, z = f.ix.grid
-    cf = orc_c.GradientField(x, y, z, f.ix.values, f.iy.values, f.iz.values)
+    x, y, z = _CPU["grid"]
+    cf = orc_c.GradientField(x, y, z, *_CPU["grads"])
     tot = {"rays": 0, "ray_rhs_evals": 0, "seconds": 0.0, "rounds": 0}
     while tot["rounds"] < max_rounds and tot["seconds"] < min_seconds:
         n = cores * 4 * rays_per_bundle
@@ -217,13 +241,17 @@ def cpu_c_port_sample(cores, rays_per_bundle, min_seconds=3.0, max_rounds=40):
                       f"RK45 default rtol=1e-3, ray-steps = nfev*rays/4; {tot['seconds']:.1f} s"}
 
 
-def cpu_line_fields(res, cores, rays_per_worker, M, kind="port"):
+def cpu_line_fields(res, cores, rays_per_worker, M, same_cube):
     steps = res["ray_rhs_evals"] / 4.0           # 4 RHS evaluations = 1 RK4-equivalent ray-step
+    kind = _CPU["kind"]
+    what = ("the reference's own ElectronCube.solve + Shadowgraphy (" + _CPU["where"] + ") under multiprocessing.Pool.map as "
+            "example_multiprocess.py:41-51" if kind == "reference" else "numpy/scipy restatement (oracle/ref_numpy.py) under Pool.map")
     return {"value": steps / res["seconds"], "unit": "ray-steps/s", "cores": cores, "kind": kind,
-            "rays_per_s": res["rays"] / res["seconds"],
-            "sample": f"{cores} processes x {res.get('rounds', 1)} bundles of {rays_per_worker} rays on the same {M}^3 "
-                      f"cube; scipy RK45 default rtol=1e-3 (reference ElectronCube.solve), ray-steps = nfev*rays/4; "
-                      f"{res['seconds']:.1f} s"}
+            "rays_per_s": res["rays"] / res["seconds"], "rays_per_bundle": rays_per_worker,
+            "cube": ("the GPU arm's own cube (same realisation)" if same_cube else
+                     "host-generated k^-11/3 GRF cube of the same size and statistics (another realisation than the GPU arm's device-Philox cube)"),
+            "sample": f"{what}; {cores} processes x {res.get('rounds', 1)} bundles of {rays_per_worker} rays on a {M}^3 "
+                      f"cube; scipy RK45 default rtol=1e-3, ray-steps = nfev*rays/4; {res['seconds']:.1f} s"}
 
 
 def run_reference_arm(args, wl):
@@ -239,7 +267,7 @@ def run_reference_arm(args, wl):
         M = ne.shape[0]
     else:
         ne = host_grf_cube(n_half)
-    cpu_reference_setup(ne, M)
+    cpu_reference_setup(ne, M, prefer_reference=not args.cpu_port)
     del ne
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(max(rays_per_worker // 4, 50), cores, min_seconds=0.0, max_rounds=1)
@@ -248,7 +276,7 @@ def run_reference_arm(args, wl):
         r = cpu_reference_step(rays_per_worker, cores, min_seconds=10.0 if args.steps == 1 else 5.0)
         for k in tot:
             tot[k] += r[k]
-    cb = cpu_line_fields(tot, cores, rays_per_worker, M)
+    cb = cpu_line_fields(tot, cores, rays_per_worker, M, bool(args.cube_file))
     try:
         cb_c = cpu_c_port_sample(cores, rays_per_worker)
     except Exception as e:                  # reported, never silently dropped
@@ -256,9 +284,10 @@ def run_reference_arm(args, wl):
     line = {"metric": "ray-steps/s", "value": cb["value"], "unit": "ray-steps/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "cores": cores,
             "rays_per_s": cb["rays_per_s"],
-            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": tot["rays"] // max(args.steps, 1)},
+            "config": {"workload": desc, "cube": f"{M}^3", "rays_per_step": tot["rays"] // max(args.steps, 1),
+                       "rays_per_bundle": rays_per_worker, "cube_realisation": cb["cube"]},
             "cpu_baseline": cb, "cpu_baseline_c": cb_c,
             "e2e": {"value": cb["value"], "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -544,6 +573,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=0, help="rays per upload chunk of the pipelined host-ray path (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="(reference arm) time the numpy/scipy restatement instead of the reference's own modules")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

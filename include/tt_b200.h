@@ -57,6 +57,10 @@ int tt_abi_version(void);
 const char* tt_last_error(void);
 /* number of CUDA devices visible, or -1 with tt_last_error() set */
 int tt_device_count(void);
+/* kernels of THIS library launched by this process so far (every successful <<<>>> of its own kernels; CUB's
+ * radix-sort passes inside tt_sort_rays are library code and not counted).  Measurement aid: bench.py reports the
+ * difference over its timed region as "gpu_launches".  No reference counterpart.                                 */
+unsigned long long tt_launch_count(void);
 
 /* ---- K1: ElectronCube.calc_dndr (particle_tracker.py:220-241) ------------------------------
  * ne_dev: the reference's C-ordered cube ne[ix][iy][iz], float (TT_F32) or double (TT_F64).

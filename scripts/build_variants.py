@@ -13,6 +13,9 @@ from turbulence_tracing_b200 import build as B
 
 VARIANTS = {
     "new": [],
+    "nopackw": ["-DTT_EVENT_PACK_W=0"],
+    "nold3": ["-DTT_EVENT_LD3=0"],
+    "base": ["-DTT_EVENT_PACK_W=0", "-DTT_EVENT_LD3=0"],
     "nomerge": ["-DTT_EVENT_MERGE=0"],
     "nofastdiv": ["-DTT_EVENT_FASTDIV=0"],
     "lean": ["-DTT_EVENT_LEAN=1"],

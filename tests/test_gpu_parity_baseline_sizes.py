@@ -39,6 +39,23 @@ def _errors(rf, ref):
     return pos, np.abs(rf[1::2] - ref[1::2]).max() / rms, rms
 
 
+def _sharp(field, s0):
+    """One step sequence per ray at rtol = 1e-13.  solve_ivp integrates far beyond the exit face, where the reference's
+    field jumps to its fill value 0 (particle_tracker.py:238-240): to accept a step across that jump the controller
+    needs h * |jump of dv/dt| <= rtol |v|, and on a 513^3 / 1025^3 cube with 30 % density fluctuations that asks of a
+    few rays in 10^4 a step below 10 ulp(t) -- solve_ivp's status -1, "step size underflow".  Those rays are integrated
+    again at rtol = 1e-11 and, if need be, 1e-9 (still 10^4 below the FP64 criterion of 1e-5)."""
+    ref = orc_c.solve(field, s0, EXTENT, "z", rtol=1e-13, atol=1e-16, batch=1, strict=False)[0]
+    for rtol in (1e-11, 1e-9):
+        bad = np.flatnonzero(~np.isfinite(ref).all(axis=0))
+        assert bad.size <= max(1, s0.shape[1] // 200), bad.size
+        if bad.size:
+            ref[:, bad] = orc_c.solve(field, np.ascontiguousarray(s0[:, bad]), EXTENT, "z", rtol=rtol, atol=rtol * 1e-3, batch=1,
+                                      strict=False)[0]
+    assert np.isfinite(ref).all()
+    return ref
+
+
 def _bench_cube(tt, n_half):
     """the cube of bench.py: device GRF (seed 1234), ne = 1e25 clip(1 + 0.3 f / sigma, 0), float32 on the device"""
     f = tt.turboGen.gaussian3D_FFT(n_half, SPECTRUM, seed=1234, dtype="float32", return_device=True).torch
@@ -66,7 +83,7 @@ def test_c3_bench_cube_production_kernel_against_c_oracle(tt):
     np.random.seed(21)
     s0 = orc.init_beam(8192, BEAM, DIV, EXTENT, "z")
     field = orc_c.make_field(ne.astype(np.float64), x, x, x)
-    ref = orc_c.solve(field, s0, EXTENT, "z", rtol=1e-13, atol=1e-16, batch=1)[0]
+    ref = _sharp(field, s0)
     del field
 
     cube32 = _cube(tt, x, ne_dev, "float32", 1)
@@ -134,7 +151,7 @@ def test_c5_cube_1025_offsets_steps_and_sub_volume_oracle(tt):
     lo, hi = 760, 960
     xs = x[lo:hi]
     sub = ne_dev[lo:hi, lo:hi, :].cpu().numpy().astype(np.float64)
-    ref = orc_c.solve(orc_c.make_field(sub, xs, xs, x), pen, EXTENT, "z", rtol=1e-13, atol=1e-16, batch=1)[0]
+    ref = _sharp(orc_c.make_field(sub, xs, xs, x), pen)
     assert np.abs(ref[0] - 3.2e-3).max() < 0.6e-3 and np.abs(ref[2] - 3.0e-3).max() < 0.6e-3   # stayed inside the sub-volume
     cube32.steps_per_cell = 1
     cube32.s0 = pen

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "tt_abi_version": (_i, []),
     "tt_last_error": (C.c_char_p, []),
     "tt_device_count": (_i, []),
+    "tt_launch_count": (C.c_ulonglong, []),
     "tt_calc_dndr": (_i, [_vp, _i, C.POINTER(_I3), C.POINTER(_D3), _i, _d, _d, _vp, _i, _vp]),
     "tt_dndr": (_i, [_vp, _i, C.POINTER(_I3), C.POINTER(_D3), C.POINTER(_D3), _i, _vp, _l, _vp, _vp]),
     "tt_init_beam": (_i, [_l, _l, _u64, _d, _d, _d, _i, _vp, _vp]),

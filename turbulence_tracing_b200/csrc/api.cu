@@ -3,9 +3,13 @@
 
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace tt {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 
@@ -68,6 +72,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 extern "C" int tt_abi_version(void) { return TT_B200_ABI_VERSION; }
 
 extern "C" const char* tt_last_error(void) { return tt::g_err; }
+
+extern "C" unsigned long long tt_launch_count(void) { return tt::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int tt_device_count(void) {
     int n = 0;

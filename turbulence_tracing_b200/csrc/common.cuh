@@ -27,15 +27,17 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                \
     } while (0)
 
-// 4-byte stream-ordered scratch word, zeroed (nullptr if the pool cannot serve it).  The device's default memory
-// pool is told ONCE to keep what it has been given (release threshold = max): with the default threshold of 0 the
-// pool hands its memory back to the driver at every synchronisation, and the next cudaMallocAsync has to map
-// fresh physical memory -- milliseconds up to (measured on a B200 VM) hundreds of milliseconds per trace launch.
+// 4-byte stream-ordered scratch word, zeroed (nullptr if it cannot be served), from a memory pool owned by this
+// library (api.cu) that keeps what it has been given: with the default pool's release threshold of 0 the pool hands
+// its memory back to the driver at every synchronisation, and the next cudaMallocAsync has to map fresh physical
+// memory -- milliseconds up to (measured on a B200 VM) hundreds of milliseconds per trace launch.
 unsigned int* scratch_flag(cudaStream_t s);
 
+void count_launch();             // api.cu: process-wide counter behind tt_launch_count()
 inline int launch_check(const char* name) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, name);
+    count_launch();
     return TT_OK;
 }
 

@@ -38,6 +38,20 @@ template <> struct GridT<float> {
         return *p;
 #endif
     }
+    // the three gradient lanes only (8 + 4 bytes).  The event kernels prefetch the next plane's corners a whole
+    // iteration ahead: with a 16-byte load the unused 4th lane is a DEAD destination register that ptxas hands
+    // out as a temporary, and the first write to it has to wait for the load in flight (write-after-write) --
+    // measured as 11.6 % of the kernel's stall samples (profiles/r02_trace_v5_c3_*) on an FFMA that does not
+    // even consume the loaded data
+    static TT_HD float4 ld3(const float4* p) {
+#ifdef __CUDA_ARCH__
+        const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+        const float b = __ldg(reinterpret_cast<const float*>(p) + 2);
+        return make_float4(a.x, a.y, b, 0.f);
+#else
+        return make_float4(p->x, p->y, p->z, 0.f);
+#endif
+    }
 };
 template <> struct GridT<double> {
     typedef double4 V4;
@@ -48,6 +62,15 @@ template <> struct GridT<double> {
         return make_double4(a.x, a.y, b.x, b.y);
 #else
         return *p;
+#endif
+    }
+    static TT_HD double4 ld3(const double4* p) {
+#ifdef __CUDA_ARCH__
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+        const double b = __ldg(reinterpret_cast<const double*>(p) + 2);
+        return make_double4(a.x, a.y, b, 0.0);
+#else
+        return make_double4(p->x, p->y, p->z, 0.0);
 #endif
     }
 };

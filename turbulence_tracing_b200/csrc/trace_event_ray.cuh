@@ -92,9 +92,9 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
         Tri<T> qx, qy, qz;
         V4 n00, n10, n01, n11;                    // corners of plane k+2 (prefetch)
         {
-            V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+            V4 c00 = GridT<T>::ld3(p), c10 = GridT<T>::ld3(p + 1), c01 = GridT<T>::ld3(p + nu), c11 = GridT<T>::ld3(p + nu + 1);
             const V4* p1 = p + plane;
-            V4 e00 = GridT<T>::ld(p1), e10 = GridT<T>::ld(p1 + 1), e01 = GridT<T>::ld(p1 + nu), e11 = GridT<T>::ld(p1 + nu + 1);
+            V4 e00 = GridT<T>::ld3(p1), e10 = GridT<T>::ld3(p1 + 1), e01 = GridT<T>::ld3(p1 + nu), e11 = GridT<T>::ld3(p1 + nu + 1);
             tri_set<T>(qx, c00.x, c10.x, c01.x, c11.x, e00.x, e10.x, e01.x, e11.x);
             tri_set<T>(qy, c00.y, c10.y, c01.y, c11.y, e00.y, e10.y, e01.y, e11.y);
             tri_set<T>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
@@ -103,7 +103,7 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
         while (true) {
             if (!have_next && k + 2 <= nw - 1) {
                 const V4* p2 = p + 2 * plane;
-                n00 = GridT<T>::ld(p2); n10 = GridT<T>::ld(p2 + 1); n01 = GridT<T>::ld(p2 + nu); n11 = GridT<T>::ld(p2 + nu + 1);
+                n00 = GridT<T>::ld3(p2); n10 = GridT<T>::ld3(p2 + 1); n01 = GridT<T>::ld3(p2 + nu); n11 = GridT<T>::ld3(p2 + nu + 1);
                 have_next = true;
             }
             // ---- stage 1 and the length of this step -------------------------------------------
@@ -179,12 +179,12 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
                 if (cross == 1) { ++cu; tu -= T(1); p += 1; } else if (cross == -1) { --cu; tu += T(1); p -= 1; }
                 else if (cross == 2) { ++cv; tv -= T(1); p += nu; } else { --cv; tv += T(1); p -= nu; }
                 if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }   // side exit
-                const V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+                const V4 c00 = GridT<T>::ld3(p), c10 = GridT<T>::ld3(p + 1), c01 = GridT<T>::ld3(p + nu), c11 = GridT<T>::ld3(p + nu + 1);
                 tri_base<T>(qx, c00.x, c10.x, c01.x, c11.x);
                 tri_base<T>(qy, c00.y, c10.y, c01.y, c11.y);
                 tri_base<T>(qz, c00.z, c10.z, c01.z, c11.z);
                 const V4* p1 = p + plane;                                         // its far plane, into the prefetch registers
-                n00 = GridT<T>::ld(p1); n10 = GridT<T>::ld(p1 + 1); n01 = GridT<T>::ld(p1 + nu); n11 = GridT<T>::ld(p1 + nu + 1);
+                n00 = GridT<T>::ld3(p1); n10 = GridT<T>::ld3(p1 + 1); n01 = GridT<T>::ld3(p1 + nu); n11 = GridT<T>::ld3(p1 + nu + 1);
             }
             if (SPC1 || renew) {                  // common to both: the primed half from the 4 corners of the far plane
                 tri_primed<T>(qx, n00.x, n10.x, n01.x, n11.x);
@@ -220,9 +220,9 @@ TT_HD unsigned event_ray(const typename GridT<T>::V4* __restrict__ grid, const d
                 if (cross == 1) { ++cu; tu -= T(1); p += 1; } else if (cross == -1) { --cu; tu += T(1); p -= 1; }
                 else if (cross == 2) { ++cv; tv -= T(1); p += nu; } else { --cv; tv += T(1); p -= nu; }
                 if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }   // side exit
-                V4 c00 = GridT<T>::ld(p), c10 = GridT<T>::ld(p + 1), c01 = GridT<T>::ld(p + nu), c11 = GridT<T>::ld(p + nu + 1);
+                V4 c00 = GridT<T>::ld3(p), c10 = GridT<T>::ld3(p + 1), c01 = GridT<T>::ld3(p + nu), c11 = GridT<T>::ld3(p + nu + 1);
                 const V4* p1 = p + plane;
-                V4 e00 = GridT<T>::ld(p1), e10 = GridT<T>::ld(p1 + 1), e01 = GridT<T>::ld(p1 + nu), e11 = GridT<T>::ld(p1 + nu + 1);
+                V4 e00 = GridT<T>::ld3(p1), e10 = GridT<T>::ld3(p1 + 1), e01 = GridT<T>::ld3(p1 + nu), e11 = GridT<T>::ld3(p1 + nu + 1);
                 tri_set<T>(qx, c00.x, c10.x, c01.x, c11.x, e00.x, e10.x, e01.x, e11.x);
                 tri_set<T>(qy, c00.y, c10.y, c01.y, c11.y, e00.y, e10.y, e01.y, e11.y);
                 tri_set<T>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
@@ -321,6 +321,42 @@ TT_HD void tri2_primed(Tri2& q, f32x2 n00, f32x2 n10, f32x2 n01, f32x2 n11) {
     q.a1 = sub2(n00, q.a); q.b1 = sub2(eb, q.b); q.c1 = sub2(sub2(n01, n00), q.c);
     q.d1 = sub2(sub2(sub2(n11, n01), eb), q.d);
 }
+// ONE trilinear polynomial (the scalar g_w lane) evaluated with packed operations: its bilinear coefficients ride as the
+// pairs (a, c) and (b, d), so that  a + tu b  and  c + tu d  are one FFMA2.  Per lane these are the operations of
+// Tri<float> / tri_at / bil_eval in the same order (bit-identical); 7 scalar FFMA per evaluation become 3 FFMA2 + 1 FFMA,
+// and on sm_100 an FFMA costs almost as much operand bandwidth as an FFMA2 (scripts/ubench_fp32_pipe.cu: 1.7 vs 2.9
+// cycles per sub-partition with three register operands)
+#ifndef TT_EVENT_PACK_W
+#define TT_EVENT_PACK_W 1
+#endif
+struct TriP {
+    f32x2 ac, bd, ac1, bd1;
+};
+struct BilP {
+    f32x2 ac, bd;
+};
+TT_HD BilP trip_at(const TriP& q, f32x2 FW) {
+    BilP r;
+    r.ac = fma2(FW, q.ac1, q.ac); r.bd = fma2(FW, q.bd1, q.bd);
+    return r;
+}
+TT_HD float bilp_eval(const BilP& q, float tu, float tv) {
+    const f32x2 r = fma2(bc2(tu), q.bd, q.ac);          // (a + tu b, c + tu d)
+    return fmaf(tv, hi2(r), lo2(r));
+}
+TT_HD void trip_base(TriP& q, float c00, float c10, float c01, float c11) {
+    const f32x2 bt = sub2(pk2(c10, c11), pk2(c00, c01));          // (b, c11 - c01)
+    q.ac = pk2(c00, c01 - c00);
+    q.bd = pk2(lo2(bt), hi2(bt) - lo2(bt));
+}
+TT_HD void trip_base_step(TriP& q) {
+    q.ac = add2(q.ac, q.ac1); q.bd = add2(q.bd, q.bd1);
+}
+TT_HD void trip_primed(TriP& q, float n00, float n10, float n01, float n11) {
+    const f32x2 e = sub2(pk2(n10, n11), pk2(n00, n01));           // (eb, n11 - n01)
+    q.ac1 = sub2(pk2(n00, n01 - n00), q.ac);
+    q.bd1 = sub2(pk2(lo2(e), hi2(e) - lo2(e)), q.bd);
+}
 #define TT_XY(v) pk2((v).x, (v).y)
 #define TT_ZW(v) pk2((v).z, (v).w)
 
@@ -347,6 +383,10 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                                const TraceArgs& A, const float4* __restrict__ aux4, double* __restrict__ aux_out,
                                const AuxArgs& AX, bool& deferred) {
     typedef float T;
+#ifndef TT_EVENT_LD3
+#define TT_EVENT_LD3 1
+#endif
+#define TT_LDN(q) ((AUX || !TT_EVENT_LD3) ? GridT<float>::ld(q) : GridT<float>::ld3(q))     // 4th lane (ne/nc) only when it is used
     unsigned steps = 0;
     const int nu = A.n[0], nv = A.n[1], nw = A.n[2];
     const long long plane = A.plane_elems;
@@ -390,20 +430,35 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
     if (fast && k < nw - 1) {
         const float4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
         Tri2 qxy;                 // (g_u, g_v) lanes, packed
-        Tri<float> qz;            // g_w, scalar (packing it with the unused ne/nc lane would only
-                                  // add work to the FP32 pipe, which is what bounds this kernel)
+#if TT_EVENT_PACK_W
+        TriP qz;                  // g_w: one polynomial, its coefficient pairs (a, c), (b, d) packed
+#define TT_QZ_AT(fwv) trip_at(qz, bc2(fwv))
+#define TT_QZ_EVAL(bil, tuv_) bilp_eval(bil, lo2(tuv_), hi2(tuv_))
+#define TT_QZ_BASE(c00, c10, c01, c11) trip_base(qz, c00, c10, c01, c11)
+#define TT_QZ_STEP() trip_base_step(qz)
+#define TT_QZ_PRIMED(n00, n10, n01, n11) trip_primed(qz, n00, n10, n01, n11)
+        typedef BilP BilZ;
+#else
+        Tri<float> qz;            // g_w, scalar
+#define TT_QZ_AT(fwv) tri_at<float>(qz, fwv)
+#define TT_QZ_EVAL(bil, tuv_) bil_eval<float>(bil, lo2(tuv_), hi2(tuv_))
+#define TT_QZ_BASE(c00, c10, c01, c11) tri_base<float>(qz, c00, c10, c01, c11)
+#define TT_QZ_STEP() tri_base_step<float>(qz)
+#define TT_QZ_PRIMED(n00, n10, n01, n11) tri_primed<float>(qz, n00, n10, n01, n11)
+        typedef Bil<float> BilZ;
+#endif
         Tri2 qzw, bxy, bzk;       // AUX: (g_w, ne/nc), (B_u, B_v), (B_w, kappa)
         const bool has_b = AUX && aux4 != nullptr;
         const float4* pa = has_b ? aux4 + (p - grid) : nullptr;
         float4 n00, n10, n01, n11;
         // (re)build the polynomials of the current cell from planes k and k+1
         auto load_cell = [&]() {
-            float4 c00 = GridT<float>::ld(p), c10 = GridT<float>::ld(p + 1), c01 = GridT<float>::ld(p + nu), c11 = GridT<float>::ld(p + nu + 1);
+            float4 c00 = TT_LDN(p), c10 = TT_LDN(p + 1), c01 = TT_LDN(p + nu), c11 = TT_LDN(p + nu + 1);
             const float4* p1 = p + plane;
-            float4 e00 = GridT<float>::ld(p1), e10 = GridT<float>::ld(p1 + 1), e01 = GridT<float>::ld(p1 + nu), e11 = GridT<float>::ld(p1 + nu + 1);
+            float4 e00 = TT_LDN(p1), e10 = TT_LDN(p1 + 1), e01 = TT_LDN(p1 + nu), e11 = TT_LDN(p1 + nu + 1);
             tri2_set(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11), TT_XY(e00), TT_XY(e10), TT_XY(e01), TT_XY(e11));
             if (AUX) tri2_set(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11), TT_ZW(e00), TT_ZW(e10), TT_ZW(e01), TT_ZW(e11));
-            else tri_set<float>(qz, c00.z, c10.z, c01.z, c11.z, e00.z, e10.z, e01.z, e11.z);
+            else { TT_QZ_BASE(c00.z, c10.z, c01.z, c11.z); TT_QZ_PRIMED(e00.z, e10.z, e01.z, e11.z); }
             if (has_b) {
                 c00 = GridT<float>::ld(pa); c10 = GridT<float>::ld(pa + 1); c01 = GridT<float>::ld(pa + nu); c11 = GridT<float>::ld(pa + nu + 1);
                 const float4* q1 = pa + plane;
@@ -418,7 +473,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
         auto load_next = [&]() {
             if (k + 2 <= nw - 1) {
                 const float4* p2 = p + 2 * plane;
-                n00 = GridT<float>::ld(p2); n10 = GridT<float>::ld(p2 + 1); n01 = GridT<float>::ld(p2 + nu); n11 = GridT<float>::ld(p2 + nu + 1);
+                n00 = TT_LDN(p2); n10 = TT_LDN(p2 + 1); n01 = TT_LDN(p2 + nu); n11 = TT_LDN(p2 + nu + 1);
             }
         };
         load_next();
@@ -428,7 +483,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
         while (true) {
             if (!have_next && k + 2 <= nw - 1) {
                 const float4* p2 = p + 2 * plane;
-                n00 = GridT<float>::ld(p2); n10 = GridT<float>::ld(p2 + 1); n01 = GridT<float>::ld(p2 + nu); n11 = GridT<float>::ld(p2 + nu + 1);
+                n00 = TT_LDN(p2); n10 = TT_LDN(p2 + 1); n01 = TT_LDN(p2 + nu); n11 = TT_LDN(p2 + nu + 1);
                 have_next = true;
             }
 #endif
@@ -449,7 +504,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 if (has_b) { b1 = bil2_eval(tri2_at(bxy, FW), TU, TV); b2 = bil2_eval(tri2_at(bzk, FW), TU, TV); }
                 aux_integrands(hi2(gzw), b1, b2, duv, dw, hq, has_b, fp1, ff1, fa1);
             } else {
-                adw = bil_eval<float>(tri_at<float>(qz, fw), lo2(tuv), hi2(tuv)) * hq;
+                adw = TT_QZ_EVAL(TT_QZ_AT(fw), tuv) * hq;
             }
             const T fw_t = SPC1 ? 1.f : ((j + 1 == spc) ? 1.f : (T)(j + 1) * hsub);
             T h = fw_t - fw;
@@ -478,13 +533,13 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
             q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
             TU = bc2(lo2(suv)); TV = bc2(hi2(suv));
             const Bil2 mxy = tri2_at(qxy, bc2(sw));             // stages 2 and 3 share their w-fraction
-            Bil<float> mz;
+            BilZ mz;
             Bil2 mzw, mb1, mb2;
             if (AUX) {
                 mzw = tri2_at(qzw, bc2(sw));
                 if (has_b) { mb1 = tri2_at(bxy, bc2(sw)); mb2 = tri2_at(bzk, bc2(sw)); }
             } else {
-                mz = tri_at<float>(qz, sw);
+                mz = TT_QZ_AT(sw);
             }
             const f32x2 bUV = CUBIC ? mul2(duv2, bc2(q)) : mul2(mul2(RUV, duv2), bc2(q));
             const f32x2 bduv = mul2(bil2_eval(mxy, TU, TV), bc2(hq));
@@ -496,7 +551,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 if (has_b) { b1 = bil2_eval(mb1, TU, TV); b2 = bil2_eval(mb2, TU, TV); }
                 aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp2, ff2, fa2);
             } else {
-                bdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq;
+                bdw = TT_QZ_EVAL(mz, suv) * hq;
             }
             suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
             q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
@@ -511,7 +566,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 if (has_b) { b1 = bil2_eval(mb1, TU, TV); b2 = bil2_eval(mb2, TU, TV); }
                 aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp3, ff3, fa3);
             } else {
-                cdw = bil_eval<float>(mz, lo2(suv), hi2(suv)) * hq;
+                cdw = TT_QZ_EVAL(mz, suv) * hq;
             }
             suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw); sw = fw + h;
             q = trcp<T>(dw2); hq = hw * q; ok = ok && dw2 > 0.f;
@@ -527,7 +582,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 if (has_b) { b1 = bil2_eval(tri2_at(bxy, FW), TU, TV); b2 = bil2_eval(tri2_at(bzk, FW), TU, TV); }
                 aux_integrands(hi2(gzw), b1, b2, duv2, dw2, hq, has_b, fp4, ff4, fa4);
             } else {
-                edw = bil_eval<float>(tri_at<float>(qz, sw), lo2(suv), hi2(suv)) * hq;
+                edw = TT_QZ_EVAL(TT_QZ_AT(sw), suv) * hq;
             }
             const T h6 = h * T(1.0 / 6.0);
             const f32x2 H6 = bc2(h6), TWO = bc2(2.f);
@@ -553,7 +608,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                     if (++k >= nw - 1) break;
                     p += plane;
                     tri2_base_step(qxy);                              // plane k+1 becomes the base plane
-                    if (AUX) tri2_base_step(qzw); else tri_base_step<float>(qz);
+                    if (AUX) tri2_base_step(qzw); else TT_QZ_STEP();
                     if (has_b) { pa += plane; tri2_base_step(bxy); tri2_base_step(bzk); }
                 } else {
                     renew = false;
@@ -568,10 +623,10 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 tuv = pk2(tu, tv);
                 if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
                 {                                                     // base plane of the new cell column
-                    const float4 c00 = GridT<float>::ld(p), c10 = GridT<float>::ld(p + 1), c01 = GridT<float>::ld(p + nu), c11 = GridT<float>::ld(p + nu + 1);
+                    const float4 c00 = TT_LDN(p), c10 = TT_LDN(p + 1), c01 = TT_LDN(p + nu), c11 = TT_LDN(p + nu + 1);
                     tri2_base(qxy, TT_XY(c00), TT_XY(c10), TT_XY(c01), TT_XY(c11));
                     if (AUX) tri2_base(qzw, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11));
-                    else tri_base<float>(qz, c00.z, c10.z, c01.z, c11.z);
+                    else TT_QZ_BASE(c00.z, c10.z, c01.z, c11.z);
                 }
                 if (has_b) {
                     pa += dp;
@@ -580,12 +635,12 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                     tri2_base(bzk, TT_ZW(c00), TT_ZW(c10), TT_ZW(c01), TT_ZW(c11));
                 }
                 const float4* p1 = p + plane;                         // its far plane, into the prefetch registers
-                n00 = GridT<float>::ld(p1); n10 = GridT<float>::ld(p1 + 1); n01 = GridT<float>::ld(p1 + nu); n11 = GridT<float>::ld(p1 + nu + 1);
+                n00 = TT_LDN(p1); n10 = TT_LDN(p1 + 1); n01 = TT_LDN(p1 + nu); n11 = TT_LDN(p1 + nu + 1);
             }
             if (SPC1 || renew) {                                      // common to both: the primed half from the far plane
                 tri2_primed(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
                 if (AUX) tri2_primed(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
-                else tri_primed<float>(qz, n00.z, n10.z, n01.z, n11.z);
+                else TT_QZ_PRIMED(n00.z, n10.z, n01.z, n11.z);
                 if (has_b) {
                     const float4* q1 = pa + plane;
                     const float4 b00 = GridT<float>::ld(q1), b10 = GridT<float>::ld(q1 + 1), b01 = GridT<float>::ld(q1 + nu), b11 = GridT<float>::ld(q1 + nu + 1);
@@ -614,7 +669,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
 #endif
                     tri2_advance(qxy, TT_XY(n00), TT_XY(n10), TT_XY(n01), TT_XY(n11));
                     if (AUX) tri2_advance(qzw, TT_ZW(n00), TT_ZW(n10), TT_ZW(n01), TT_ZW(n11));
-                    else tri_advance<float>(qz, n00.z, n10.z, n01.z, n11.z);
+                    else { TT_QZ_STEP(); TT_QZ_PRIMED(n00.z, n10.z, n01.z, n11.z); }
                     if (has_b) {
                         pa += plane;
                         const float4* q1 = pa + plane;
@@ -680,6 +735,12 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
     }
     return steps;
 }
+#undef TT_LDN
+#undef TT_QZ_AT
+#undef TT_QZ_EVAL
+#undef TT_QZ_BASE
+#undef TT_QZ_STEP
+#undef TT_QZ_PRIMED
 #undef TT_XY
 #undef TT_ZW
 

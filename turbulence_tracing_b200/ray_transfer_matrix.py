@@ -372,8 +372,14 @@ class Rays:
 class Shadowgraphy(Rays):
     """Two-lens M = 1 telescope, apertures of radius R at both lenses (:208-227)."""
 
-    def solve(self):
+    def solve(self, displacement=None):
+        """``displacement`` is the keyword of the reference's stale example scripts
+        (``sh.solve(displacement=0)``, example_MPI.py:71-72, example_multiprocess.py:69): the object plane's offset
+        from the focal plane of the first lens in mm, i.e. what the checked-in class takes as ``focal_plane`` at
+        construction (:160-172).  None keeps the constructor's value."""
         L, R = self.L, self.R
+        if displacement is not None:
+            self.focal_plane = displacement
         self._set_program([
             _op_distance(L - self.focal_plane), _op(_lib.OP_CIRC_APERTURE, R), _op_lens(L, L),
             _op_distance(L * 2),
