@@ -339,6 +339,8 @@ def run_gpu_arm(args, wl):
         c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=args.steps_per_cell, keep_sf=False, verbose=False,
                             B_on=aux, inv_brems=aux, phaseshift=aux)
         c.kernel_variant = args.variant
+        if args.no_face_grid:
+            c.face_grid = False
         if aux:
             c.external_B(Bvec)
             c.external_Te(Te)
@@ -572,6 +574,7 @@ def main():
     ap.add_argument("--cube-file", default="", help="(reference arm) .npy ne cube to trace instead of a host GRF")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="rays per upload chunk of the pipelined host-ray path (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-face-grid", action="store_true", help="trace over the float4 corner grid (tt_trace) instead of the face-coefficient grid")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-port", action="store_true", help="(reference arm) time the numpy/scipy restatement instead of the reference's own modules")
     args = ap.parse_args()

@@ -121,6 +121,24 @@ int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_d
              const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
              unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
 
+/* ---- K2f: the production path of ElectronCube.solve in TT_F32 at 1 step per cell ------------------------------
+ * Same reference function as tt_trace (particle_tracker.py:312-331 solve, :398-419 dsdt, :333-380 ray_at_exit), same
+ * arguments, outputs, status flags and ray order; the trilinear look-up of dsdt (:243-256) reads a second, derived
+ * grid: per cell FACE (iw, cell row, cell column) the bilinear coefficients (A, B, C, D) of the three gradient
+ * components, g(tu, tv) = A + tu B + tv (C + tu D), with the step-size factors folded in -- three 16-byte words
+ *   (A_u, A_v, B_u, B_v) (C_u, C_v, D_u, D_v) (A_w, C_w, B_w, D_w),   scaled by h_w^2/h_u, h_w^2/h_v, h_w
+ * = 48 (nu-1)(nv-1) nw bytes (tt_face_grid_bytes), formed ONCE per calc_dndr by tt_build_face_grid from the float4
+ * grid of tt_calc_dndr instead of once per ray and plane inside the trace kernel.  tt_trace_faces marches every ray
+ * over it (one RK4 step per cell, steps ending on cell faces as in tt_trace variant 3) and hands unusual rays (outside
+ * / steep / side exit / time cap / non-finite) to the same general kernel over grid4_dev.  status_dev is required.
+ * p->dtype must be TT_F32 and p->steps_per_cell 1; p->variant is ignored.                                         */
+size_t tt_face_grid_bytes(const int n_xyz[3], int par);
+int tt_build_face_grid(const void* grid4_dev, const int n_xyz[3], const double spacing_xyz[3], int par,
+                       void* faces_dev, tt_stream_t stream);
+int tt_trace_faces(const tt_trace_params* p, const void* grid4_dev, const void* faces_dev, const double* s0_dev,
+                   long np, const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
+                   unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
+
 /* ---- magnetised / absorbing extension (BASELINE config 4) --------------------------------------
  * Evidence in the reference: call sites only (example_kitchensink.py:72-101: B_on, inv_brems,
  * phaseshift, external_B/Te/Z, Jf) -- there is no implementation in the checkout, so parity is

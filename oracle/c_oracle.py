@@ -55,6 +55,9 @@ def load():
         lib.tto_solve.argtypes = [fp, dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, dp, C.c_int,
                                   C.POINTER(C.c_long)]
         lib.tto_solve.restype = C.c_longlong
+        lib.tto_solve_ms.argtypes = [fp, dp, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, dp, C.c_int,
+                                     C.POINTER(C.c_long)]
+        lib.tto_solve_ms.restype = C.c_longlong
         lib.tto_ray_at_exit.argtypes = [dp, C.c_long, C.c_double, C.c_int, dp]
         lib.tto_ray_at_exit.restype = None
         lib.tto_max_threads.restype = C.c_int
@@ -114,13 +117,16 @@ def ray_at_exit(sf, extent, probing_direction="z"):
     return rf
 
 
-def solve(field, s0, extent, probing_direction="z", rtol=1e-3, atol=1e-6, batch=None, threads=0, strict=True):
+def solve(field, s0, extent, probing_direction="z", rtol=1e-3, atol=1e-6, batch=None, threads=0, strict=True,
+          max_step=np.inf):
     """Same contract as ``oracle.ref_numpy.solve``: (rf, sf, ray_rhs_evals).
 
     ``batch=None`` is the reference's ``ElectronCube.solve`` (one adaptive step sequence for the whole
     bundle, particle_tracker.py:317-330); ``batch=k`` integrates bundles of k rays independently
     (``threads`` POSIX threads, 0 = all cores), ``batch=1`` gives every ray its own step control.
     A bundle whose step size underflows (solve_ivp's status -1) raises, or with ``strict=False`` comes back NaN.
+    ``max_step`` (seconds) is solve_ivp's option of that name; the reference leaves it at infinity.  See tt_oracle.c:
+    the sharp reference of the parity tests uses one cell's transit time (``cell_transit_time``).
     """
     lib = load()
     s0 = _f64(s0)
@@ -128,13 +134,18 @@ def solve(field, s0, extent, probing_direction="z", rtol=1e-3, atol=1e-6, batch=
     sf = np.empty_like(s0)
     T = np.sqrt(8.0) * float(extent) / C_LIGHT
     failed = C.c_long()
-    evals = lib.tto_solve(C.byref(field.c), _p(s0), n, int(batch or n), T, float(rtol), float(atol), _p(sf),
-                          int(threads), C.byref(failed))
+    evals = lib.tto_solve_ms(C.byref(field.c), _p(s0), n, int(batch or n), T, float(rtol), float(atol), float(max_step),
+                             _p(sf), int(threads), C.byref(failed))
     if evals < 0:
         raise MemoryError("tto_solve: out of memory")
     if failed.value and strict:
         raise RuntimeError(f"tto_solve: step size underflow in {failed.value} bundle(s)")
     return ray_at_exit(sf, extent, probing_direction), sf, int(evals)
+
+
+def cell_transit_time(x, y, z):
+    """time light needs across the smallest cell: the ``max_step`` of the sharp reference"""
+    return min(float(np.diff(np.asarray(a, dtype=np.float64)).min()) for a in (x, y, z)) / C_LIGHT
 
 
 def solve_one_bundle(field, s0, extent, rtol=1e-3, atol=1e-6, t_hist=None):

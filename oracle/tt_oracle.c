@@ -203,8 +203,15 @@ static double rms_ratio(const double* num, const double* scale, long N, double m
  * y0, y_out: (6, n) row-major.  Returns nfev (>0), or -1 on allocation failure, -2 if the step size
  * underflowed (solve_ivp status -1).  n_steps / n_rejected / t_hist (the accepted step end times, at most
  * t_cap of them) are optional diagnostics. */
-long tto_solve_ivp_rk45(const tto_field* F, const double* y0, long n, double T, double rtol, double atol, double* y_out,
-                        long* n_steps, long* n_rejected, double* t_hist, long t_cap) {
+/* max_step: solve_ivp's option of that name (scipy/integrate/_ivp/rk.py: RungeKutta.__init__ -> validate_max_step,
+ * _step_impl: "if self.h_abs > max_step: h_abs = max_step", select_initial_step bounded by it as well).  The reference
+ * leaves it at its default, infinity (particle_tracker.py:322).  The sharp reference of the parity tests sets it to one
+ * cell's transit time: behind an exactly flat stretch of the field (ne clipped to 0 over a few cells, free space) the
+ * error estimate is 0, the step grows tenfold per step, and a millimetre-long step whose seven stage points all happen
+ * to land in flat spots again is accepted at ANY rtol -- it leaps over the structure in between (observed on the
+ * 513^3 benchmark cube: 8 of 8192 rays off by 0.1 .. 0.4 micrometres at rtol = 1e-13 while rtol = 1e-12 is right). */
+long tto_solve_ivp_rk45_ms(const tto_field* F, const double* y0, long n, double T, double rtol, double atol, double max_step,
+                           double* y_out, long* n_steps, long* n_rejected, double* t_hist, long t_cap) {
     const long N = 6 * n;
     if (n <= 0) return 0;
     double* buf = (double*)malloc(sizeof(double) * (size_t)N * 12);
@@ -232,13 +239,14 @@ long tto_solve_ivp_rk45(const tto_field* F, const double* y0, long n, double T, 
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
         else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
-        h_abs = fmin(fmin(100 * h0, h1), T);
+        h_abs = fmin(fmin(fmin(100 * h0, h1), T), max_step);
     }
     double t_old = 0.0;
     int failed = 0;
     while (t < T) {                                        /* solver.status == 'running' */
         const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
+        if (h_abs > max_step) h_abs = max_step;
+        else if (h_abs < min_step) h_abs = min_step;
         int step_rejected = 0;
         double h, t_new;
         for (;;) {
@@ -312,6 +320,11 @@ long tto_solve_ivp_rk45(const tto_field* F, const double* y0, long n, double T, 
     return failed ? -2 : nfev;
 }
 
+long tto_solve_ivp_rk45(const tto_field* F, const double* y0, long n, double T, double rtol, double atol, double* y_out,
+                        long* n_steps, long* n_rejected, double* t_hist, long t_cap) {
+    return tto_solve_ivp_rk45_ms(F, y0, n, T, rtol, atol, INFINITY, y_out, n_steps, n_rejected, t_hist, t_cap);
+}
+
 /* Many bundles of `batch` rays each (the last one may be shorter), one solve_ivp call per bundle like the
  * reference run under multiprocessing.Pool (example_multiprocess.py:41-51); bundles are handed out to
  * `threads` POSIX threads (this image's gcc has no libgomp).  s0, sf: (6, n) row-major.  Returns the sum
@@ -323,7 +336,7 @@ typedef struct {
     const double* s0;
     double* sf;
     long n, batch, nb;
-    double T, rtol, atol;
+    double T, rtol, atol, max_step;
     long next;                 /* next bundle to hand out (guarded by mu) */
     long long total;
     int bad;                   /* 1: allocation failure */
@@ -344,7 +357,7 @@ static void* solve_worker(void* arg) {
         if (in) {
             double* out = in + 6 * m;
             for (int k = 0; k < 6; ++k) memcpy(in + k * m, J->s0 + (size_t)k * n + lo, sizeof(double) * (size_t)m);
-            nfev = tto_solve_ivp_rk45(J->F, in, m, J->T, J->rtol, J->atol, out, NULL, NULL, NULL, 0);
+            nfev = tto_solve_ivp_rk45_ms(J->F, in, m, J->T, J->rtol, J->atol, J->max_step, out, NULL, NULL, NULL, 0);
             if (nfev >= 0)
                 for (int k = 0; k < 6; ++k) memcpy(J->sf + (size_t)k * n + lo, out + k * m, sizeof(double) * (size_t)m);
             else if (nfev == -2)
@@ -366,14 +379,14 @@ int tto_max_threads(void) {
     return c > 0 ? (int)c : 1;
 }
 
-long long tto_solve(const tto_field* F, const double* s0, long n, long batch, double T, double rtol, double atol,
-                    double* sf, int threads, long* n_failed) {
+long long tto_solve_ms(const tto_field* F, const double* s0, long n, long batch, double T, double rtol, double atol,
+                       double max_step, double* sf, int threads, long* n_failed) {
     if (n_failed) *n_failed = 0;
     if (n <= 0) return 0;
     if (batch <= 0 || batch > n) batch = n;
     solve_job J;
     J.F = F; J.s0 = s0; J.sf = sf; J.n = n; J.batch = batch; J.nb = (n + batch - 1) / batch;
-    J.T = T; J.rtol = rtol; J.atol = atol; J.next = 0; J.total = 0; J.bad = 0; J.n_failed = 0;
+    J.T = T; J.rtol = rtol; J.atol = atol; J.max_step = max_step > 0 ? max_step : INFINITY; J.next = 0; J.total = 0; J.bad = 0; J.n_failed = 0;
     pthread_mutex_init(&J.mu, NULL);
     if (threads <= 0) threads = tto_max_threads();
     if (threads > J.nb) threads = (int)J.nb;
@@ -391,6 +404,11 @@ long long tto_solve(const tto_field* F, const double* s0, long n, long batch, do
     pthread_mutex_destroy(&J.mu);
     if (n_failed) *n_failed = J.n_failed;
     return J.bad ? -(long long)J.bad : J.total;
+}
+
+long long tto_solve(const tto_field* F, const double* s0, long n, long batch, double T, double rtol, double atol,
+                    double* sf, int threads, long* n_failed) {
+    return tto_solve_ms(F, s0, n, batch, T, rtol, atol, INFINITY, sf, threads, n_failed);
 }
 
 /* ElectronCube.ray_at_exit, particle_tracker.py:345-380.  dir: 0 = 'x', 1 = 'y', 2 = 'z'. */

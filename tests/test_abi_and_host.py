@@ -202,8 +202,14 @@ def test_bench_reference_arm_contract():
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["unit"] == "ray-steps/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the reference's own modules (oracle/_ref after `make -C oracle ref`, or /root/reference in the build container);
+    # "port" only where neither exists
+    from oracle import reference_live as live
+    assert line["cpu_baseline"]["kind"] == ("reference" if live.available() else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+    port = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--cpu-port",
+                           "--steps", "1", "--warmup", "0", "--cpu-rays", "40"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert json.loads(port.stdout.strip().splitlines()[-1])["cpu_baseline"]["kind"] == "port"
 
 
 def test_device_array_numpy_semantics_on_cpu_tensor():

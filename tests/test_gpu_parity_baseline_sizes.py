@@ -40,18 +40,24 @@ def _errors(rf, ref):
 
 
 def _sharp(field, s0):
-    """One step sequence per ray at rtol = 1e-13.  solve_ivp integrates far beyond the exit face, where the reference's
-    field jumps to its fill value 0 (particle_tracker.py:238-240): to accept a step across that jump the controller
-    needs h * |jump of dv/dt| <= rtol |v|, and on a 513^3 / 1025^3 cube with 30 % density fluctuations that asks of a
-    few rays in 10^4 a step below 10 ulp(t) -- solve_ivp's status -1, "step size underflow".  Those rays are integrated
-    again at rtol = 1e-11 and, if need be, 1e-9 (still 10^4 below the FP64 criterion of 1e-5)."""
-    ref = orc_c.solve(field, s0, EXTENT, "z", rtol=1e-13, atol=1e-16, batch=1, strict=False)[0]
+    """The sharp reference: scipy's RK45 (C restatement), one step sequence per ray, rtol = 1e-13, and solve_ivp's
+    ``max_step`` option set to one cell's transit time.  Both departures from a plain tight-rtol run were forced by
+    the 513^3 benchmark cube (ne clipped at 0 in its deepest troughs; measured on the host):
+      * behind an exactly flat stretch of the field the error estimate is 0, the step grows tenfold per step, and a
+        millimetre-long step whose stage points all land in flat spots again is accepted at any rtol: 21 of 8192 rays
+        came back 2e-9 .. 4e-7 m off (rtol 1e-12 and 1e-8 disagreed with rtol 1e-13 on them) -- hence max_step;
+      * solve_ivp integrates far beyond the exit face, where the reference's field jumps to its fill value 0
+        (particle_tracker.py:238-240); to accept a step across that jump the controller needs h |jump of dv/dt| <=
+        rtol |v|, which for a few rays in 10^4 is a step below 10 ulp(t): status -1, "step size underflow".  Those
+        rays are integrated again at rtol = 1e-11 and, if need be, 1e-9 (still 10^4 below the FP64 criterion)."""
+    ms = orc_c.cell_transit_time(field.x, field.y, field.z)
+    ref = orc_c.solve(field, s0, EXTENT, "z", rtol=1e-13, atol=1e-16, batch=1, strict=False, max_step=ms)[0]
     for rtol in (1e-11, 1e-9):
         bad = np.flatnonzero(~np.isfinite(ref).all(axis=0))
         assert bad.size <= max(1, s0.shape[1] // 200), bad.size
         if bad.size:
             ref[:, bad] = orc_c.solve(field, np.ascontiguousarray(s0[:, bad]), EXTENT, "z", rtol=rtol, atol=rtol * 1e-3, batch=1,
-                                      strict=False)[0]
+                                      strict=False, max_step=ms)[0]
     assert np.isfinite(ref).all()
     return ref
 
@@ -287,3 +293,67 @@ def test_density_setups_dsdt_and_solve_through_the_product_api(tt, kind, kw):
     print(f"test_{kind}: {ok.sum()} rays, {p:.1e} m, angle {a:.1e} of rms ({rms * 1e3:.3f} mrad)")
     assert p <= 1e-5 * 3e-3
     assert a <= 1e-5 or np.abs(rf[1::2, ok] - ref[1::2, ok]).max() <= 1e-9
+
+
+def test_face_coefficient_kernel_against_corner_grid_kernel_and_abi(tt):
+    """tt_build_face_grid / tt_trace_faces (the production path of solve() in float32 at 1 step per cell) against
+    tt_trace on the same grid: 257^3 bench cube, 2e6 rays of the bench beam + a wide divergent beam whose side-exit
+    rays both hand to the general kernel; sf with and without; non-cubic cells probing y."""
+    import torch
+    from turbulence_tracing_b200 import _lib
+    pt = tt.particle_tracker
+    ne = _bench_cube(tt, 128)
+    M = ne.shape[0]
+    x = np.linspace(-EXTENT, EXTENT, M)
+    out = {}
+    for fg in (True, False):
+        cube = pt.ElectronCube(x, x, x, dtype="float32", verbose=False, face_grid=fg)
+        cube.external_ne(ne)
+        cube.calc_dndr()
+        cube.init_beam(2_000_000, BEAM, DIV, seed=3)
+        rf = cube.solve().torch.clone()
+        assert (cube._faces is not None) == fg
+        assert int((cube.status.torch == 1).sum()) == 2_000_000 and cube.ray_steps == (M - 1) * 2_000_000
+        sf = cube.sf.torch.clone()
+        np.random.seed(9)
+        cube.s0 = orc.init_beam(200_000, 5.5e-3, 1e-2, EXTENT, "z")          # wide, divergent: side exits, misses
+        rfw = cube.solve().torch.clone()
+        out[fg] = (rf, sf, rfw, cube.status.torch.clone(), cube.ray_steps)
+    a, b = out[True], out[False]
+    d = float((a[0][0::2] - b[0][0::2]).abs().max())
+    da = float((a[0][1::2] - b[0][1::2]).abs().max())
+    print(f"face-coefficient kernel vs corner-grid kernel, 257^3, 2e6 rays: {d:.1e} m = {d / PIXEL_M:.1e} pixel, angles {da:.1e} rad")
+    assert d <= 2e-4 * PIXEL_M and da <= 1e-8
+    assert float((a[1][:3] - b[1][:3]).abs().max()) <= 1e-8 and float((a[1][3:] - b[1][3:]).abs().max()) <= 1e-6 * orc.C_LIGHT
+    assert torch.equal(a[3], b[3])                      # same rays marched / handed over / missed
+    assert 0 < int((a[3] != 1).sum()) < 200_000 and a[4] == b[4] or abs(a[4] - b[4]) <= 1e-4 * b[4]
+    m = torch.isfinite(b[2]).all(dim=0)
+    assert torch.equal(m, torch.isfinite(a[2]).all(dim=0))
+    dw = float((a[2][0::2, m] - b[2][0::2, m]).abs().max())
+    print(f"wide beam (side exits through the general kernel): {dw:.1e} m")
+    assert dw <= 2e-4 * PIXEL_M
+
+    # non-cubic cells, probing y, against the C oracle through the product API
+    xx, yy, zz = np.linspace(-5e-3, 5e-3, 97), np.linspace(-5e-3, 5e-3, 129), np.linspace(-5e-3, 5e-3, 81)
+    ne2 = orc.density("exponential_cos", xx, yy, zz, n_e0=3e24, Ly=2e-3, s=4e-3)
+    cube = pt.ElectronCube(xx, yy, zz, "y", dtype="float32", verbose=False, face_grid=True)
+    cube.external_ne(ne2)
+    cube.calc_dndr()
+    np.random.seed(6)
+    cube.init_beam(4096, 3e-3, 1e-3)
+    s0 = cube.s0.copy()
+    rf = np.asarray(cube.solve())
+    assert np.all(np.asarray(cube.status) == 1)
+    ref = orc_c.solve(orc_c.make_field(ne2, xx, yy, zz), s0, EXTENT, "y", rtol=1e-13, atol=1e-16, batch=1, strict=False)[0]
+    ok = np.isfinite(ref).all(axis=0)
+    p, ang, _ = _errors(rf[:, ok], ref[:, ok])
+    print(f"face kernel, non-cubic cells, probing y vs C oracle: {p:.2e} m = {p / PIXEL_M:.1e} pixel")
+    assert ok.mean() > 0.99 and p <= 1e-3 * PIXEL_M
+
+    # face_grid=True where it does not apply is an error, not a silent switch
+    c64 = pt.ElectronCube(x, x, x, dtype="float64", verbose=False, face_grid=True)
+    c64.external_ne(ne)
+    c64.calc_dndr()
+    c64.init_beam(10, BEAM, DIV, seed=1)
+    with pytest.raises(ValueError):
+        c64.solve()

@@ -897,3 +897,116 @@ def test_rectilinear_body_on_uniform_axes_equals_uniform_body(host_lib, event_li
         r32 = _run(host_lib, G32, x, x, x, 2, float(g["extent"]), s0, spc)[0]
         u32 = _run_uniform(event_lib, G32, x, x, x, 2, float(g["extent"]), s0, spc)[0]
         assert np.abs(r32[0::2] - u32[0::2]).max() <= 1e-3 * 52.3e-6
+
+
+# ------------------------------------------------------------------------------------------- face-coefficient kernel
+@pytest.fixture(scope="module")
+def face_lib(tmp_path_factory):
+    lib = _build_host(tmp_path_factory, "trace_face_host")
+    vp = C.c_void_p
+    lib.host_build_face_grid.argtypes = [vp, C.POINTER(C.c_int * 3), C.POINTER(C.c_double * 3), C.c_int, vp]
+    lib.host_build_face_grid.restype = C.c_int
+    lib.host_trace_faces.argtypes = [vp, vp, C.POINTER(C.c_int * 3), C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 3), C.c_int,
+                                     C.c_double, C.c_double, vp, C.c_long, vp, vp, vp, C.POINTER(C.c_ulonglong),
+                                     C.POINTER(C.c_long), C.c_int]
+    lib.host_trace_faces.restype = C.c_int
+    return lib
+
+
+def _run_faces(lib, G, x, y, z, par, extent, s0, want_sf=True, second_pass=True):
+    n = s0.shape[1]
+    s0 = np.ascontiguousarray(s0, dtype=np.float64)
+    rf, sf = np.full((4, n), np.nan), np.full((6, n), np.nan)
+    status = np.zeros(n, dtype=np.uint8)
+    steps, nd = C.c_ulonglong(), C.c_long()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    dims = (C.c_int * 3)(len(x), len(y), len(z))
+    org = (C.c_double * 3)(x[0], y[0], z[0])
+    h = (C.c_double * 3)(*[(a[-1] - a[0]) / (len(a) - 1) for a in (x, y, z)])
+    nw, nv, nu = G.shape[:3]
+    faces = np.full((nw, nv - 1, nu - 1, 12), np.nan, dtype=np.float32)
+    assert lib.host_build_face_grid(p(G), C.byref(dims), C.byref(h), par, p(faces)) == 0
+    assert np.isfinite(faces).all()
+    rc = lib.host_trace_faces(p(G), p(faces), C.byref(dims), C.byref(org), C.byref(h), par, float(extent),
+                              float(np.sqrt(8.0) * extent), p(s0), n, p(rf), p(sf) if want_sf else None, p(status),
+                              C.byref(steps), C.byref(nd), int(second_pass))
+    assert rc == 0
+    return rf, sf, status, steps.value, nd.value, faces
+
+
+def test_face_grid_builder_source(face_lib):
+    """face_grid_cell: (A, B, C, D) of every cell face = FP64 differences of the float4 node grid times the folded
+    step-size factors, in the word order the kernel loads"""
+    rng = np.random.default_rng(3)
+    xx, yy, zz = np.linspace(-5e-3, 5e-3, 9), np.linspace(-4e-3, 4e-3, 7), np.linspace(-5e-3, 5e-3, 6)
+    for par in (0, 1, 2):
+        fa = FRAME[par]
+        n = [len(a) for a in (xx, yy, zz)]
+        G = rng.standard_normal((n[fa[2]], n[fa[1]], n[fa[0]], 4)).astype(np.float32)
+        s0 = np.zeros((6, 1))
+        faces = _run_faces(face_lib, G, xx, yy, zz, par, 5e-3, s0)[5]
+        h = [(a[-1] - a[0]) / (len(a) - 1) for a in (xx, yy, zz)]
+        hu, hv, hw = (h[a] for a in fa)
+        sc = [float(np.float32(hw / hu)) * hw, float(np.float32(hw / hv)) * hw, hw]
+        g = G.astype(np.float64)
+        c00, c10, c01, c11 = g[:, :-1, :-1], g[:, :-1, 1:], g[:, 1:, :-1], g[:, 1:, 1:]
+        A, B, Cc, D = c00, c10 - c00, c01 - c00, ((c11 - c01) - c10) + c00
+        want = np.empty(faces.shape)
+        for m, s in enumerate(sc[:2]):
+            want[..., 0 + m], want[..., 2 + m], want[..., 4 + m], want[..., 6 + m] = s * A[..., m], s * B[..., m], s * Cc[..., m], s * D[..., m]
+        want[..., 8], want[..., 9], want[..., 10], want[..., 11] = sc[2] * A[..., 2], sc[2] * Cc[..., 2], sc[2] * B[..., 2], sc[2] * D[..., 2]
+        np.testing.assert_array_equal(faces, want.astype(np.float32))
+
+
+def test_face_kernel_body_on_the_host(face_lib, packed_lib):
+    """face_ray_f32x2 -- the body of trace_face_kernel_f32x2, the kernel the benchmark runs -- on a 129^3 k^-11/3 cube:
+    within 1e-3 detector pixel of the C oracle, every ray marched to the far face, ray-steps = 128 per ray, and within
+    FP32 rounding of the corner-grid production kernel (same integrator, same events)."""
+    import bench
+    from oracle import ref_numpy as orc
+    ne = bench.host_grf_cube(64, seed=21)
+    x = np.linspace(-5e-3, 5e-3, 129)
+    np.random.seed(4)
+    s0 = orc.init_beam(2048, 4e-3, 0.05e-3, 5e-3, "z")
+    G = _grid4(ne, x, x, x, 2, np.float32)
+    ref = orc_c.solve(orc_c.make_field(ne, x, x, x), s0, 5e-3, "z", rtol=1e-13, atol=1e-16, batch=1)[0]
+    a = _run_faces(face_lib, G, x, x, x, 2, 5e-3, s0)
+    b = _run_packed(packed_lib, G, x, x, x, 2, 5e-3, s0, 1)
+    assert a[3] == 128 * s0.shape[1] and a[4] == 0 and np.all(a[2] == EXIT_FACE)
+    p, ang = _errors(a[0], ref)
+    d = np.abs(a[0][0::2] - b[0][0::2]).max()
+    print(f"face kernel body: {p:.2e} m = {p / 52.3e-6:.1e} pixel, angle {ang:.1e} of rms; vs corner-grid kernel {d:.1e} m")
+    assert p <= 1e-3 * 52.3e-6 and d <= 2e-4 * 52.3e-6
+    # sf (state at time T) and the no-sf instantiation
+    sfd = np.abs(a[1] - b[1])
+    assert sfd[:3].max() <= 1e-8 and sfd[3:].max() <= 1e-6 * C_LIGHT
+    a2 = _run_faces(face_lib, G, x, x, x, 2, 5e-3, s0, want_sf=False)
+    np.testing.assert_array_equal(a2[0], a[0])
+
+
+@pytest.mark.parametrize("direction,par", [("x", 0), ("y", 1), ("z", 2)])
+def test_face_kernel_body_non_cubic_cells_and_deferred_rays(face_lib, packed_lib, direction, par):
+    """non-cubic cells (the folded h_w/h_u, h_w/h_v factors), every probing direction, a wide divergent beam: rays that
+    miss the cube or leave sideways are handed over exactly as by the corner-grid kernel, the rest agree with the C oracle"""
+    from oracle import ref_numpy as orc
+    xx, yy, zz = np.linspace(-5e-3, 5e-3, 41), np.linspace(-5e-3, 5e-3, 57), np.linspace(-5e-3, 5e-3, 33)
+    ne2 = orc.density("exponential_cos", xx, yy, zz, n_e0=3e24, Ly=2e-3, s=4e-3)
+    np.random.seed(6)
+    s1 = orc.init_beam(1024, 5.2e-3, 2e-2, 5e-3, direction)
+    G2 = _grid4(ne2, xx, yy, zz, par, np.float32)
+    a = _run_faces(face_lib, G2, xx, yy, zz, par, 5e-3, s1, second_pass=False)
+    b = _run_packed(packed_lib, G2, xx, yy, zz, par, 5e-3, s1, 1)
+    assert 0 < a[4] < s1.shape[1]
+    np.testing.assert_array_equal(a[2] == DEFERRED, b[2] == DEFERRED)
+    m = a[2] == EXIT_FACE
+    d = np.abs(a[0][:, m][0::2] - b[0][:, m][0::2]).max()
+    ref2 = orc_c.solve(orc_c.make_field(ne2, xx, yy, zz), s1[:, m], 5e-3, direction, rtol=1e-13, atol=1e-16, batch=1, strict=False)[0]
+    ok = np.all(np.isfinite(ref2), axis=0)
+    p, ang = _errors(a[0][:, m][:, ok], ref2[:, ok])
+    pb, _ = _errors(b[0][:, m][:, ok], ref2[:, ok])
+    print(f"probing {direction}, non-cubic cells, 1 step per cell: face kernel {p:.2e} m, corner-grid kernel {pb:.2e} m, difference {d:.1e} m")
+    assert p <= max(1e-3 * 52.3e-6, 1.5 * pb) and d <= 2e-4 * 52.3e-6
+    # with the second pass every ray has an answer, and the deferred ones carry the gather kernel's flags
+    c = _run_faces(face_lib, G2, xx, yy, zz, par, 5e-3, s1)
+    assert not np.any(c[2] == DEFERRED)
+    np.testing.assert_array_equal(c[0][:, m], a[0][:, m])

@@ -196,3 +196,30 @@ def test_c_oracle_reports_scipys_crawl_instead_of_hanging():
         orc_c.solve(field, s0[:, :1], 5e-3, "x", rtol=1e-13, atol=1e-16, batch=1)
     # at the reference's default tolerances the same ray is no problem
     assert np.all(np.isfinite(orc_c.solve(field, s0, 5e-3, "x")[0]))
+
+
+def test_c_max_step_is_solve_ivps_max_step(golden):
+    """the ``max_step`` option of the C restatement against scipy's own solve_ivp(max_step=...) on the same bundle:
+    same result and, at the default rtol, the same number of RHS evaluations (every accept / reject decision; at tight
+    tolerances the error estimate is a cancellation and the two implementations' step sequences part in the last bits,
+    as without max_step); max_step = inf is the plain call"""
+    from scipy.integrate import solve_ivp
+    g = golden("solve_default")
+    x = np.linspace(-5e-3, 5e-3, int(g["n"]))
+    ne = orc.density("exponential_cos", x, x, x, n_e0=2e23, Ly=1e-3, s=4e-3)
+    fc, fn = orc_c.make_field(ne, x, x, x), orc.make_field(ne, x, x, x)
+    s0 = np.ascontiguousarray(g["s0"][:, :40])
+    T = np.sqrt(8.0) * x.max() / orc.C_LIGHT
+    ms = 3 * orc_c.cell_transit_time(x, x, x)
+    for rtol, atol in ((1e-3, 1e-6), (1e-9, 1e-12)):
+        rf, sf, evals = orc_c.solve(fc, s0, x.max(), "z", rtol=rtol, atol=atol, max_step=ms)
+        sol = solve_ivp(lambda t, y: orc.dsdt(t, y, fn), [0, T], s0.flatten(), t_eval=[0.0, T], method="RK45", rtol=rtol, atol=atol,
+                        max_step=ms)
+        if rtol == 1e-3:
+            assert evals == sol.nfev * s0.shape[1]
+        np.testing.assert_allclose(sf, sol.y[:, -1].reshape(6, -1), rtol=1e-10 if rtol == 1e-3 else 1e-7, atol=1e-12)
+        assert sol.nfev >= 6 * T / ms                                 # the limit binds: at least T / max_step steps
+    a = orc_c.solve(fc, s0, x.max(), "z")
+    b = orc_c.solve(fc, s0, x.max(), "z", max_step=np.inf)
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[2] == b[2]

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "tt_sort_rays_workspace": (_i, [_l, C.POINTER(_sz)]),
     "tt_sort_rays": (_i, [_vp, _l, _i, C.POINTER(_D3), C.POINTER(_D3), C.POINTER(_I3), _vp, _vp, _sz, _vp]),
     "tt_trace": (_i, [C.POINTER(TraceParams), _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tt_face_grid_bytes": (_sz, [C.POINTER(_I3), _i]),
+    "tt_build_face_grid": (_i, [_vp, C.POINTER(_I3), C.POINTER(_D3), _i, _vp, _vp]),
+    "tt_trace_faces": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
                           _vp, _vp]),
     "tt_calc_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp]),

@@ -70,8 +70,8 @@ __global__ void dndr_kernel(const typename GridT<T>::V4* __restrict__ grid, Trac
     dndr_point<T>(grid, A, pos, npts, i, out);
 }
 
-static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3],
-                     const double spacing_xyz[3], int par) {
+int fill_trace_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3],
+                    const double spacing_xyz[3], int par) {
     TT_REQUIRE(n_xyz && origin_xyz && spacing_xyz, "null geometry pointer");
     TT_REQUIRE(par >= 0 && par <= 2, "par must be 0, 1 or 2 (got %d)", par);
     Frame f = frame_of(par);
@@ -89,6 +89,18 @@ static int fill_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3
     return TT_OK;
 }
 
+// second pass of the event-marching paths: the general (cell-cache gather) kernel over the rays flagged TT_RAY_DEFERRED,
+// on a small grid; returns at once on the device when A.any_deferred says there are none
+int launch_trace_second_pass(int dtype, const void* grid4, const double* s0, const uint32_t* perm, double* rf, double* sf,
+                             unsigned long long* ray_steps, uint8_t* status, const TraceArgs& A, cudaStream_t s) {
+    const int block = 128;
+    long blocks = (A.np + block - 1) / block;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (dtype == TT_F32) trace_kernel<float, 0><<<(unsigned)blocks, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A, 1);
+    else trace_kernel<double, 0><<<(unsigned)blocks, block, 0, s>>>((const double4*)grid4, s0, perm, rf, sf, ray_steps, status, A, 1);
+    return launch_check("trace_kernel");
+}
+
 }  // namespace tt
 
 extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_dev, long np,
@@ -102,7 +114,7 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     TT_REQUIRE(p->s_max > 0 && p->extent == p->extent, "tt_trace: s_max must be > 0");
     TT_REQUIRE(np < (1L << 32) || !perm_dev, "tt_trace: perm is 32-bit; trace in bundles of < 2^32 rays");
     TraceArgs A;
-    int rc = fill_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
+    int rc = fill_trace_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
     if (rc) return rc;
     A.extent = p->extent; A.s_max = p->s_max; A.spc = p->steps_per_cell; A.np = np;
     if (np == 0) return TT_OK;
@@ -154,7 +166,7 @@ extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, co
     TT_REQUIRE(np < (1L << 32) || !perm_dev, "tt_trace_aux: perm is 32-bit; trace in bundles of < 2^32 rays");
     TT_REQUIRE(a->omega > 0 && a->nc > 0, "tt_trace_aux: omega and nc must be > 0");
     TraceArgs A;
-    int rc = fill_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
+    int rc = fill_trace_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
     if (rc) return rc;
     A.extent = p->extent; A.s_max = p->s_max; A.spc = p->steps_per_cell; A.np = np;
     if (np == 0) return TT_OK;
@@ -197,7 +209,7 @@ extern "C" int tt_dndr(const void* grid4_dev, int grid_dtype, const int n_xyz[3]
     TT_REQUIRE(grid4_dev && pos_dev && out_dev, "tt_dndr: null pointer");
     TT_REQUIRE(grid_dtype == TT_F32 || grid_dtype == TT_F64, "tt_dndr: dtype must be TT_F32 or TT_F64");
     TraceArgs A;
-    int rc = fill_args(A, n_xyz, origin_xyz, spacing_xyz, par);
+    int rc = fill_trace_args(A, n_xyz, origin_xyz, spacing_xyz, par);
     if (rc) return rc;
     A.extent = 0; A.s_max = 0; A.spc = 1; A.np = npts;
     if (npts <= 0) return TT_OK;

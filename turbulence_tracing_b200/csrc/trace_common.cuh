@@ -407,6 +407,11 @@ struct AuxArgs {
 };
 
 
+// trace.cu: frame geometry of a launch; the general kernel over the rays an event kernel deferred
+int fill_trace_args(TraceArgs& A, const int n_xyz[3], const double origin_xyz[3], const double spacing_xyz[3], int par);
+int launch_trace_second_pass(int dtype, const void* grid4, const double* s0, const uint32_t* perm, double* rf, double* sf,
+                             unsigned long long* ray_steps, uint8_t* status, const TraceArgs& A, cudaStream_t s);
+
 // event-marching kernels (trace_event.cu).  aux_out != nullptr selects the variant that also carries the
 // passive quantities (FP32 only).  packed = FP32x2 arithmetic (FP32 only).
 int launch_trace_event(int dtype, bool packed, int steps_per_cell, const void* grid4, const double* s0,

@@ -1,0 +1,122 @@
+// tt_face_grid_bytes / tt_build_face_grid / tt_trace_faces: event marching over the face-coefficient grid
+// (trace_face_ray.cuh), the production FP32 kernel at 1 step per cell.
+#include "trace_face_ray.cuh"
+
+#pragma nv_diag_suppress 550
+
+namespace tt {
+
+#ifndef TT_FACE_BLOCK
+#define TT_FACE_BLOCK 128
+#endif
+#ifndef TT_FACE_MIN_BLOCKS
+#define TT_FACE_MIN_BLOCKS 5
+#endif
+
+// one thread per face cell, u fastest: reads 4 corners (L1 serves the overlap), writes 48 contiguous bytes
+__global__ void __launch_bounds__(256)
+face_grid_kernel(const float4* __restrict__ grid, float4* __restrict__ faces, int nu, int nv, int nw, double su, double sv,
+                 double sw) {
+    const int nuc = nu - 1, nvc = nv - 1;
+    const long long plane = (long long)nu * nv;
+    const long long total = (long long)nuc * nvc * nw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cu = (int)(i % nuc);
+        const long long r = i / nuc;
+        const int cv = (int)(r % nvc), k = (int)(r / nvc);
+        float4 out[3];
+        face_grid_cell(grid, nu, plane, cu, cv, k, su, sv, sw, out);
+        float4* o = faces + 3 * i;
+        o[0] = out[0]; o[1] = out[1]; o[2] = out[2];
+    }
+}
+
+template <bool TRACK_S>
+__global__ void __launch_bounds__(TT_FACE_BLOCK, TT_FACE_MIN_BLOCKS)
+trace_face_kernel_f32x2(const float4* __restrict__ faces, const double* __restrict__ s0, const uint32_t* __restrict__ perm,
+                        double* __restrict__ rf, double* __restrict__ sf, unsigned long long* __restrict__ ray_steps,
+                        uint8_t* __restrict__ status, TraceArgs A, FaceArgs FA) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned steps = 0;
+    if (tid < A.np) {
+        const long ray = perm ? (long)perm[tid] : tid;
+        bool deferred = false;
+        steps = face_ray_f32x2<TRACK_S>(faces, s0, ray, rf, sf, status, A, FA, deferred);
+        if (deferred && A.any_deferred) *A.any_deferred = 1u;       // (benign race: everybody stores 1)
+    }
+    if (ray_steps) {
+        unsigned v = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(ray_steps, (unsigned long long)v);
+    }
+}
+
+int launch_trace_face(const void* faces, const double* s0, const uint32_t* perm, double* rf, double* sf,
+                      unsigned long long* ray_steps, uint8_t* status, const TraceArgs& A, cudaStream_t s) {
+    FaceArgs FA;
+    fill_face_args(FA, A);
+    const int block = TT_FACE_BLOCK;
+    const unsigned blocks = (unsigned)((A.np + block - 1) / block);
+    if (sf) trace_face_kernel_f32x2<true><<<blocks, block, 0, s>>>((const float4*)faces, s0, perm, rf, sf, ray_steps, status, A, FA);
+    else trace_face_kernel_f32x2<false><<<blocks, block, 0, s>>>((const float4*)faces, s0, perm, rf, sf, ray_steps, status, A, FA);
+    return launch_check("trace_face_kernel_f32x2");
+}
+
+}  // namespace tt
+
+extern "C" size_t tt_face_grid_bytes(const int n_xyz[3], int par) {
+    if (!n_xyz || par < 0 || par > 2 || n_xyz[0] < 2 || n_xyz[1] < 2 || n_xyz[2] < 2) return 0;
+    const tt::Frame f = tt::frame_of(par);
+    return 48ull * (size_t)(n_xyz[f.a[0]] - 1) * (size_t)(n_xyz[f.a[1]] - 1) * (size_t)n_xyz[f.a[2]];
+}
+
+extern "C" int tt_build_face_grid(const void* grid4_dev, const int n_xyz[3], const double spacing_xyz[3], int par,
+                                  void* faces_dev, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(grid4_dev && faces_dev && n_xyz && spacing_xyz, "tt_build_face_grid: null pointer");
+    TT_REQUIRE(par >= 0 && par <= 2, "tt_build_face_grid: par must be 0, 1 or 2 (got %d)", par);
+    const Frame f = frame_of(par);
+    int n[3];
+    double h[3];
+    for (int k = 0; k < 3; ++k) {
+        n[k] = n_xyz[f.a[k]]; h[k] = spacing_xyz[f.a[k]];
+        TT_REQUIRE(n[k] >= 2, "tt_build_face_grid: every axis needs >= 2 points");
+        TT_REQUIRE(h[k] > 0, "tt_build_face_grid: spacing must be > 0");
+    }
+    double su, sv, sw;
+    face_scales(h, su, sv, sw);
+    const long long total = (long long)(n[0] - 1) * (n[1] - 1) * n[2];
+    const int block = 256;
+    long long blocks = (total + block - 1) / block;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    face_grid_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>((const float4*)grid4_dev, (float4*)faces_dev, n[0], n[1],
+                                                                          n[2], su, sv, sw);
+    return launch_check("face_grid_kernel");
+}
+
+extern "C" int tt_trace_faces(const tt_trace_params* p, const void* grid4_dev, const void* faces_dev, const double* s0_dev,
+                              long np, const uint32_t* perm_dev, double* rf_dev, double* sf_dev,
+                              unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream) {
+    using namespace tt;
+    TT_REQUIRE(p && grid4_dev && faces_dev && s0_dev && rf_dev && status_dev, "tt_trace_faces: null pointer");
+    TT_REQUIRE(np >= 0, "tt_trace_faces: negative ray count");
+    TT_REQUIRE(p->dtype == TT_F32, "tt_trace_faces: the face-coefficient grid is FP32 (use tt_trace for TT_F64)");
+    TT_REQUIRE(p->steps_per_cell == 1, "tt_trace_faces: 1 step per cell (use tt_trace for more)");
+    TT_REQUIRE(p->s_max > 0 && p->extent == p->extent, "tt_trace_faces: s_max must be > 0");
+    TT_REQUIRE(np < (1L << 32) || !perm_dev, "tt_trace_faces: perm is 32-bit; trace in bundles of < 2^32 rays");
+    TraceArgs A;
+    int rc = fill_trace_args(A, p->n_xyz, p->origin_xyz, p->spacing_xyz, p->par);
+    if (rc) return rc;
+    A.extent = p->extent; A.s_max = p->s_max; A.spc = 1; A.np = np;
+    if (np == 0) return TT_OK;
+    const long blocks = (np + TT_FACE_BLOCK - 1) / TT_FACE_BLOCK;
+    TT_REQUIRE(blocks < (1L << 31), "tt_trace_faces: too many rays for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int* flag = scratch_flag(s);
+    A.any_deferred = flag;
+    rc = launch_trace_face(faces_dev, s0_dev, perm_dev, rf_dev, sf_dev, ray_steps_dev, status_dev, A, s);
+    if (rc == TT_OK) rc = launch_trace_second_pass(TT_F32, grid4_dev, s0_dev, perm_dev, rf_dev, sf_dev, ray_steps_dev, status_dev, A, s);
+    if (flag) cudaFreeAsync(flag, s);
+    return rc;
+}

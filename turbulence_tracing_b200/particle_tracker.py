@@ -72,7 +72,7 @@ class ElectronCube:
     """A class to hold and generate electron density cubes (particle_tracker.py:121-145)."""
 
     def __init__(self, x, y, z, *args, probing_direction=None, B_on=False, inv_brems=False, phaseshift=False,
-                 dtype="float32", steps_per_cell=1, sort_rays=True, keep_sf=True, verbose=True):
+                 dtype="float32", steps_per_cell=1, sort_rays=True, keep_sf=True, verbose=True, face_grid="auto"):
         """x, y, z: 1-D coordinate arrays (m); probing_direction 'x' | 'y' | 'z' (4th positional argument or
         keyword, default 'z'; :125-145).
 
@@ -108,6 +108,12 @@ class ElectronCube:
         self.verbose = bool(verbose)
         self._ne = None          # host array or device tensor as supplied
         self._grid = None        # device tensor [nw, nv, nu, 4]
+        # face-coefficient grid of the production FP32 kernel (tt_build_face_grid / tt_trace_faces: 48 B per cell face,
+        # built lazily by solve() from the gradient grid).  "auto": used when it applies (float32, uniform axes,
+        # 1 step per cell, trajectory only) and fits next to everything else; True: required; False: never
+        self.face_grid = face_grid
+        self._faces = None
+        self._faces_valid = False
         self._nodes = None       # device node coordinates (x, y, z) when the axes are not uniformly spaced
         self._s0 = None
         self.ray_steps = 0       # RK4 steps taken inside the cube by the last solve()
@@ -307,7 +313,26 @@ class ElectronCube:
                                         par, float(self.nc), float(ne_max), _lib.ptr(grid),
                                         _lib.dtype_code(gdt), _lib.stream_ptr()), "tt_calc_dndr")
         self._grid, self._frame, self._origin, self._spacing = grid, fa, origin, spacing
+        self._faces_valid = False
         self.dndx_interp, self.dndy_interp, self.dndz_interp = (_GradInterp(self, k) for k in range(3))
+
+    def _face_grid(self):
+        """The face-coefficient grid of the current gradient grid (built on first use after calc_dndr, in place when
+        the cube was only refreshed), or None when ``face_grid="auto"`` and it does not fit into free device memory."""
+        torch = _lib.torch_cuda()
+        lib = _lib.load()
+        if self._faces is not None and self._faces_valid:
+            return self._faces
+        nbytes = int(lib.tt_face_grid_bytes(_lib.i3(self.shape), self._par))
+        if self._faces is None or self._faces.numel() * 4 != nbytes:
+            self._faces = None
+            if self.face_grid == "auto" and nbytes + (8 << 30) > torch.cuda.mem_get_info()[0]:
+                return None
+            self._faces = torch.empty(nbytes // 4, dtype=torch.float32, device="cuda")
+        _lib.check(lib.tt_build_face_grid(_lib.ptr(self._grid), _lib.i3(self.shape), _lib.d3(self._spacing), self._par,
+                                          _lib.ptr(self._faces), _lib.stream_ptr()), "tt_build_face_grid")
+        self._faces_valid = True
+        return self._faces
 
     def _require_grid(self):
         if self._grid is None:
@@ -436,6 +461,14 @@ class ElectronCube:
         if use_aux:
             ap = _lib.AuxParams(float(self.omega), float(self.nc), float(self.VerdetConst))
             aux4 = self._aux_grid()
+        faces = None
+        applies = (nodes is None and not use_aux and grid.dtype == torch.float32 and self.steps_per_cell == 1
+                   and p.variant == 0)
+        if self.face_grid is True and not applies:
+            raise ValueError("face_grid=True needs float32, uniformly spaced axes, steps_per_cell=1 and no B_on / "
+                             "inv_brems / phaseshift")
+        if self.face_grid and applies:
+            faces = self._face_grid()
         steps = torch.zeros(1, dtype=torch.int64, device="cuda")
         events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
 
@@ -463,6 +496,10 @@ class ElectronCube:
                 _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0b), n,
                                             _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out),
                                             _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace_aux")
+            elif faces is not None:
+                _lib.check(lib.tt_trace_faces(C.byref(p), _lib.ptr(grid), _lib.ptr(faces), _lib.ptr(s0b), n, _lib.ptr(perm),
+                                              _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream),
+                           "tt_trace_faces")
             else:
                 _lib.check(lib.tt_trace(C.byref(p), _lib.ptr(grid), _lib.ptr(s0b), n, _lib.ptr(perm), _lib.ptr(rf),
                                         _lib.ptr(sf), _lib.ptr(steps), _lib.ptr(status), stream), "tt_trace")
