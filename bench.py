@@ -39,7 +39,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ALGO_BYTES_PER_RAY_STEP = 512      # 4 RK4 stages x 8 trilinear corners x 16 B (float4), FP32 mode
 WORKLOADS = {
     # name: (N_half of gaussian3D_FFT -> M = 2N+1 points per axis, rays per GPU, BASELINE config)
     "c3": (256, 100_000_000, "configs[2]: 513^3 (gaussian3D_FFT N=256) k^-11/3 GRF ne cube, 1e8 rays per GPU, shadowgraphy"),
@@ -105,19 +104,6 @@ class ClockSampler:
             pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
-
-
-def measured_traffic(workload, dtype, variant, full=False):
-    """dram bytes per trace launch from the committed ncu capture of this configuration, or None
-    (full=True: the whole ncu summary of that capture)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            e = json.load(f)["entries"].get(f"{workload}/{dtype}/{variant or 3}")
-        if full:
-            return e
-        return (e["dram_bytes_per_launch"] / 1e9) if e else None
-    except Exception:
-        return None
 
 
 def measured_hbm_peak():
@@ -294,31 +280,119 @@ def run_reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def run_gpu_arm(args, wl):
-    import torch
-    from turbulence_tracing_b200 import distributed as ttd
-    from turbulence_tracing_b200 import particle_tracker as pt, ray_transfer_matrix as rtm, turboGen as tg
-    from turbulence_tracing_b200 import _lib
+TRACE_KERNELS = {       # (mangled-name substring, display name) of the kernel that dominates a step, per (dtype, aux, faces)
+    ("float32", False, True): ("trace_face_kernel_f32x2ILb0", "trace_face_kernel_f32x2<false>"),
+    ("float32", False, False): ("trace_event_kernel_f32x2ILb1ELb0ELb1ELb0", "trace_event_kernel_f32x2<1,0,1,0>"),
+    ("float32", True, False): ("trace_event_kernel_f32x2ILb1ELb1ELb1ELb1", "trace_event_kernel_f32x2<1,1,1,1>"),
+    ("float64", False, False): ("trace_event_kernelIdLb1", "trace_event_kernel<double,true>"),
+}
 
-    rank, world, local = ttd.init_from_env()
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    dev = torch.device("cuda", local)
-    _lib.load(build_if_missing=False)
-    n_half, rays, desc = WORKLOADS[wl]
-    if args.rays:
-        rays = args.rays
+
+def kernel_sass_sha(mangled_substr):
+    """sha256 of the SASS text of one kernel of the LOADED libtt_b200.so (cuobjdump), or None.  profiles/traffic.json
+    stamps every ncu-derived entry with it, so a stale instruction mix cannot be applied to a rebuilt kernel."""
+    import hashlib
+    import re
+    import shutil
+    from turbulence_tracing_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-sass", _lib.lib_path()], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    h, on, found = hashlib.sha256(), False, False
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = mangled_substr in m.group(1)
+            found = found or on
+            continue
+        if on:
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+            if m:
+                h.update(m.group(1).strip().encode())
+    return h.hexdigest() if found else None
+
+
+def profile_entry(key):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)["entries"].get(key)
+    except Exception:
+        return None
+
+
+def build_roofline(key, kern, steps_per_launch, kernel_ms, clocks, bytes_per_step, bytes_note):
+    """Primary bound of the trace kernels: the FP32 (FMA) pipe.  The kernels keep the cell's polynomial in registers and
+    load 48 B (one cell face) per ray-step from L1/L2, so HBM carries a few % of its bandwidth and an HBM fraction says
+    nothing (it is reported as `hbm_algorithmic` for SURVEY section 8d, with the measured DRAM traffic beside it).
+    achieved = ray-steps/s / 32 x (FMA-pipe issue slots per warp and ray-step, from the ncu opcode mix of THIS build:
+    the entry in profiles/traffic.json carries the sha256 of the kernel's SASS, checked against the loaded library) x
+    64 flop per slot (32 lanes x FMA); peak = 148 SMs x 4 sub-partitions x 1 slot per clock x sampled SM clock."""
+    mangled, name = kern
+    e = profile_entry(key) or {}
+    sha = kernel_sass_sha(mangled)
+    stale = None if sha is None or not e.get("sass_sha256") else (sha != e["sass_sha256"])
+    peak_hbm, peak_src = measured_hbm_peak()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    slots = e.get("fma_pipe_slots_per_warp_step")
+    warp_steps_per_s = steps_per_launch / 32.0 / (kernel_ms * 1e-3)
+    peak_slots = 148 * 4 * sm_mhz * 1e6
+    r = {"bound": "fp32_pipe", "kernel": name, "unit": "TFLOP/s", "kernel_ms": kernel_ms,
+         "ray_steps_per_launch": steps_per_launch,
+         "peak": peak_slots * 64 / 1e12, "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+         "achieved": None, "frac": None, "fma_pipe_slots_per_warp_step": slots, "profile": e.get("source"),
+         "profile_matches_loaded_kernel": (None if stale is None else (not stale)), "kernel_sass_sha256": sha,
+         "traffic": (e.get("dram_bytes_per_launch") / 1e9) if e.get("dram_bytes_per_launch") else None,
+         "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+         "ncu": {k: e.get(k) for k in ("ncu_kernel_ms", "fma_pipe_busy_pct", "issue_slots_busy_pct", "l1_hit_pct", "l2_hit_pct",
+                                       "dram_pct_of_peak", "warp_instructions_per_warp_step", "registers", "warps_active_pct",
+                                       "eligible_warps_per_scheduler") if k in e}}
+    if slots:
+        ach = warp_steps_per_s * slots
+        r["achieved"] = ach * 64 / 1e12
+        r["frac"] = ach / peak_slots
+        r["note"] = ("achieved = FMA-pipe issue slots/s x 64 flop (a packed FP32x2 instruction holds the pipe for 2 slots); "
+                     "frac = share of the FP32 pipe's issue cycles in use = ncu sm__pipe_fma_cycles_active")
+    alg = steps_per_launch * bytes_per_step / (kernel_ms * 1e-3) / 1e9
+    r["hbm_algorithmic"] = {"bound": "hbm", "achieved": alg, "peak": peak_hbm, "unit": "GB/s", "frac": alg / peak_hbm,
+                            "algorithmic_bytes_per_ray_step": bytes_per_step, "peak_source": peak_src,
+                            "note": bytes_note + "; rays that share a cell are served by L1/L2, DRAM carries `traffic`, so this "
+                                                 "fraction exceeds 1 and is no bound of the kernel"}
+    return r
+
+
+class GpuCtx:
+    pass
+
+
+def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup, do_e2e, sampler=None, beam=BEAM_SIZE,
+                bin_scale=10, steps_per_cell=1, face_grid=True, pageable=False, ne_cache=None):
+    """One measurement: `steps` timed passes of the hot path over this rank's `rays_per_rank` rays of workload `wl`.
+    Returns a dict (same on every rank for the reduced figures)."""
+    torch, ttd, pt, rtm, tg, _lib = ctx.torch, ctx.ttd, ctx.pt, ctx.rtm, ctx.tg, ctx.lib
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    n_half, _, desc = WORKLOADS[wl]
     M = 2 * n_half + 1
     x = np.linspace(-EXTENT, EXTENT, M)
-    dtype = args.dtype
+    lib = _lib.load()
 
     # ---- synthetic inputs: GRF cube on rank 0 (device Philox + cuFFT), NCCL broadcast ------------
     t0 = time.perf_counter()
-    ne = torch.empty((M, M, M), dtype=torch.float32, device=dev)
-    if rank == 0:
-        f = tg.gaussian3D_FFT(n_half, SPECTRUM, seed=1234, dtype="float32", return_device=True).torch
-        ne.copy_(ne_from_field(f, torch))
-        del f
-    ttd.broadcast_cube(ne, src=0)
+    if ne_cache is not None and ne_cache.get("M") == M:
+        ne = ne_cache["ne"]
+    else:
+        if ne_cache is not None:
+            ne_cache.clear()
+            torch.cuda.empty_cache()
+        ne = torch.empty((M, M, M), dtype=torch.float32, device=dev)
+        if rank == 0:
+            f = tg.gaussian3D_FFT(n_half, SPECTRUM, seed=1234, dtype="float32", return_device=True).torch
+            ne.copy_(ne_from_field(f, torch))
+            del f
+        ttd.broadcast_cube(ne, src=0)
+        if ne_cache is not None:
+            ne_cache.update(M=M, ne=ne)
     torch.cuda.synchronize()
     t_cube = time.perf_counter() - t0
 
@@ -336,31 +410,34 @@ def run_gpu_arm(args, wl):
         ttd.broadcast_cube(Te, src=0)
 
     def make_cube():
-        c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=args.steps_per_cell, keep_sf=False, verbose=False,
-                            B_on=aux, inv_brems=aux, phaseshift=aux)
+        c = pt.ElectronCube(x, x, x, dtype=dtype, steps_per_cell=steps_per_cell, keep_sf=False, verbose=False,
+                            B_on=aux, inv_brems=aux, phaseshift=aux, face_grid="auto" if face_grid else False)
         c.kernel_variant = args.variant
-        if args.no_face_grid:
-            c.face_grid = False
         if aux:
             c.external_B(Bvec)
             c.external_Te(Te)
             c.external_Z(1.0)
         return c
 
+    rays = rays_per_rank
     cube = make_cube()
-    first, _ = ttd.shard_range(rays * world, rank, world)       # weak scaling: `rays` per rank
     cube.external_ne(ne)
-    cube.init_beam(rays, BEAM_SIZE, DIVERGENCE, seed=99, first_ray=first)
+    cube.init_beam(rays, beam, DIVERGENCE, seed=99, first_ray=first_ray)
     s0_dev = cube.s0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     trace_ms = []
-
     phase_events = []          # per step: events at the phase boundaries (read after the timed region)
 
     def mark(lst):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         lst.append(e)
+
+    def detector(rf, to_host):
+        sh = rtm.Shadowgraphy(rf)
+        sh.solve()
+        sh.histogram(bin_scale=bin_scale, to_host=to_host)
+        return sh
 
     def step_device():
         marks = []
@@ -371,9 +448,7 @@ def run_gpu_arm(args, wl):
         cube.s0 = s0_dev
         rf = cube.solve()
         mark(marks)
-        sh = rtm.Shadowgraphy(rf)
-        sh.solve()
-        sh.histogram(to_host=False)
+        sh = detector(rf, False)
         mark(marks)
         H = ttd.allreduce_histograms([sh.H_dev])[0]
         mark(marks)
@@ -389,6 +464,7 @@ def run_gpu_arm(args, wl):
         c._trace_events = []                    # CUDA events around every trace launch from here on
         if sampler:
             sampler.start()
+        l0 = int(lib.tt_launch_count())
         ev[0].record()
         counters, last = [], None
         for _ in range(steps):
@@ -396,6 +472,7 @@ def run_gpu_arm(args, wl):
             counters.append(last[1])
         ev[1].record()
         torch.cuda.synchronize()
+        launches = int(lib.tt_launch_count()) - l0
         clocks = sampler.stop() if sampler else None
         if world > 1:
             torch.distributed.barrier()
@@ -404,105 +481,187 @@ def run_gpu_arm(args, wl):
         c._trace_events = None
         ms = ttd.allreduce_scalar(float(ms), "max", device=dev)
         tot_steps = ttd.allreduce_scalar(int(sum(int(t.item()) for t in counters)), "sum", device=dev)
-        return ms, tot_steps, last, clocks
+        launches = ttd.allreduce_scalar(int(launches), "sum", device=dev)
+        return ms, tot_steps, last, clocks, launches
 
-    ms, tot_steps, last, clocks = timed(step_device, cube, args.warmup, args.steps, ClockSampler(local))
+    ms, tot_steps, last, clocks, launches = timed(step_device, cube, warmup, steps, sampler)
     kernel_ms = float(np.mean(trace_ms)) if trace_ms else float("nan")
-    names = ["calc_dndr", "sort+trace", "optics+hist", "allreduce"]
-    phases = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in phase_events[-args.steps:]]))
-              for i, n in enumerate(names)}
+    names = ["calc_dndr", "face_grid+sort+trace", "optics+hist", "allreduce"]
+    phases = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in phase_events[-steps:]])) for i, n in enumerate(names)}
     phases["trace_kernel"] = kernel_ms
     if world > 1:                        # every rank's breakdown (rank skew shows up as all-reduce wait)
         allp = [None] * world
         torch.distributed.all_gather_object(allp, phases)
         phases = allp
-    steps_per_launch = tot_steps / (args.steps * world)
-    value = tot_steps / (ms * 1e-3)
+    rays_total = ttd.allreduce_scalar(int(rays), "sum", device=dev)
     H_dev = last[0]
-    rays_per_s = rays * world * args.steps / (ms * 1e-3)
+    # ---- validity of the timed work (last step): every ray marched to the far face by the event kernel, none lost ----
+    n_exit = ttd.allreduce_scalar(int((cube.status.torch == 1).sum().item()), "sum", device=dev)
+    hist_sum = int(H_dev.sum().item())
+    expect = rays_total * (M - 1) * steps_per_cell * steps
+    checks = {"rays": rays_total, "status_exit_face": n_exit, "histogram_sum": hist_sum, "ray_steps": tot_steps,
+              "ray_steps_expected_if_all_marched": expect,
+              "ok": bool(n_exit == rays_total and tot_steps == expect and 0 < hist_sum <= rays_total)}
+    used_faces = cube._faces is not None
+    out = {"value": tot_steps / (ms * 1e-3), "ms_per_step": ms / steps, "rays_per_s": rays_total * steps / (ms * 1e-3),
+           "rays_total": rays_total, "rays_per_rank": rays, "phases_ms": phases, "kernel_ms": kernel_ms, "clocks": clocks,
+           "gpu_launches": launches, "checks": checks, "cube_setup_s": t_cube, "M": M, "aux": aux, "faces": used_faces,
+           "steps_per_launch": tot_steps / (steps * world), "desc": desc, "e2e": None, "ne": ne}
 
-    # ---- e2e: public API, host pinned buffers in, histogram + counter out --------------------------
-    e2e = None
-    if not args.no_e2e:
-        ne_host = torch.empty((M, M, M), dtype=torch.float32, pin_memory=True)
-        ne_host.copy_(ne)
-        s0_host = torch.empty((6, rays), dtype=torch.float64, pin_memory=True)
-        s0_host.copy_(s0_dev.torch)
-        torch.cuda.synchronize()
-        cube2 = make_cube()
-        if args.e2e_chunk:
-            cube2.pipeline_chunk_rays = args.e2e_chunk
-        ne_np, s0_np = ne_host.numpy(), s0_host.numpy()
+    # ---- e2e: public API, host buffers in, histogram + counter out ----------------------------------
+    if do_e2e:
+        def host_buffers(pinned):
+            ne_h = torch.empty((M, M, M), dtype=torch.float32, pin_memory=pinned)
+            ne_h.copy_(ne)
+            s0_h = torch.empty((6, rays), dtype=torch.float64, pin_memory=pinned)
+            s0_h.copy_(s0_dev.torch)
+            torch.cuda.synchronize()
+            return ne_h, s0_h
 
-        e2e_events = []
+        def run_e2e(pinned, steps_e, warm_e):
+            ne_host, s0_host = host_buffers(pinned)
+            cube2 = make_cube()
+            if args.e2e_chunk:
+                cube2.pipeline_chunk_rays = args.e2e_chunk
+            ne_np, s0_np = ne_host.numpy(), s0_host.numpy()
+            e2e_events = []
 
-        def step_e2e():
-            marks = []
-            mark(marks)
-            cube2.external_ne(ne_np)                # host numpy -> H2D inside calc_dndr
-            cube2.calc_dndr(LWL)
-            mark(marks)
-            cube2.s0 = s0_np                        # host numpy -> H2D inside solve
-            rf = cube2.solve()
-            mark(marks)
-            sh = rtm.Shadowgraphy(rf)
-            sh.solve()
-            sh.histogram()                          # D2H of the histogram inside
-            H = ttd.allreduce_histograms([sh.H_dev])[0]
-            _ = cube2.ray_steps                     # D2H of the counter
-            mark(marks)
-            e2e_events.append(marks)
-            return H, cube2._steps_dev
+            def step_e2e():
+                marks = []
+                mark(marks)
+                cube2.external_ne(ne_np)                # host numpy -> H2D inside calc_dndr
+                cube2.calc_dndr(LWL)
+                mark(marks)
+                cube2.s0 = s0_np                        # host numpy -> H2D inside solve
+                rf = cube2.solve()
+                mark(marks)
+                sh = detector(rf, True)                 # D2H of the histogram inside
+                H = ttd.allreduce_histograms([sh.H_dev])[0]
+                _ = cube2.ray_steps                     # D2H of the counter
+                mark(marks)
+                e2e_events.append(marks)
+                return H, cube2._steps_dev
 
-        ms2, tot2, _, _ = timed(step_e2e, cube2, max(2, min(args.warmup, 3)), args.steps)
-        e2e_names = ["h2d_cube+calc_dndr", "h2d_rays+sort+trace", "optics+hist+d2h"]
-        e2e = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / args.steps,
-               "phases_ms": {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in e2e_events[-args.steps:]]))
-                             for i, n in enumerate(e2e_names)},
-               "trace_launches_per_step": len(trace_ms) // max(args.steps, 1),
-               "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(args.steps, 1),
-               "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
-               "d2h_bytes_per_step": int(H_dev.numel() * 8 + 8),
-               "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
-                            "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None)},
-               "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
-        del ne_host, s0_host
+            ms2, tot2, last2, _, launches2 = timed(step_e2e, cube2, warm_e, steps_e)
+            e2e_names = ["h2d_cube+calc_dndr", "h2d_rays+face_grid+sort+trace", "optics+hist+d2h"]
+            ph = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in e2e_events[-steps_e:]])) for i, n in enumerate(e2e_names)}
+            if world > 1:
+                allp = [None] * world
+                torch.distributed.all_gather_object(allp, ph)
+                ph = allp
+            r = {"value": tot2 / (ms2 * 1e-3), "unit": "ray-steps/s", "ms_per_step": ms2 / steps_e, "steps": steps_e, "phases_ms": ph,
+                 "host_memory": "pinned (torch pin_memory)" if pinned else "pageable (plain numpy arrays, as a drop-in caller passes)",
+                 "trace_launches_per_step": len(trace_ms) // max(steps_e, 1),
+                 "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(steps_e, 1),
+                 "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
+                 "d2h_bytes_per_step": int(last2[0].numel() * 8 + 8), "gpu_launches": launches2,
+                 "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
+                              "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None)},
+                 "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
+            del ne_host, s0_host, cube2
+            return r
 
-    # ---- roofline of the dominant kernel (trace) ---------------------------------------------------
-    peak, peak_src = measured_hbm_peak()
-    # FP64: 32-byte corners; config 4: a second float4 grid (B, kappa) is gathered at every corner
-    bytes_per_step = ALGO_BYTES_PER_RAY_STEP * (2 if dtype == "float64" else 1) * (2 if aux else 1)
-    achieved = steps_per_launch * bytes_per_step / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "trace_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic(wl, dtype, args.variant) if not args.rays else None,
-                "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/traffic.json)",
-                "algorithmic_gb_per_launch": steps_per_launch * bytes_per_step / 1e9, "peak_source": peak_src,
-                "ncu": measured_traffic(wl, dtype, args.variant, full=True) if not args.rays else None,
-                "kernel_ms": kernel_ms, "ray_steps_per_launch": steps_per_launch,
-                "algorithmic_bytes_per_ray_step": bytes_per_step,
-                "note": "algorithmic bytes (4 stages x 8 corners x 16 B); the corners of a cell are held in registers "
-                        "and shared by neighbouring rays through L1/L2, so DRAM traffic is <1% of the algorithmic "
-                        "bytes (mostly the permuted s0 gather / rf scatter) and frac > 1 -- see profiles/"}
+        out["e2e"] = run_e2e(True, steps, max(2, min(warmup, 3)))
+        if pageable:
+            out["e2e_pageable"] = run_e2e(False, max(1, steps // 2), 1)
+    del cube
+    return out
 
-    # secondary bound: the FP32 pipe (what actually limits the register-resident kernel).  Static issue-cycle count
-    # per warp-step from the committed opcode mix x the live ray-step rate, against 4 FMA-pipe issue slots per SM
-    # and clock (148 SMs) at the SM clock sampled during the timed region.
-    ncu_e = roofline["ncu"] or {}
-    if ncu_e.get("fma_pipe_slots_per_warp_step") and clocks and clocks.get("sm_mhz"):
-        slots = ncu_e["fma_pipe_slots_per_warp_step"]
-        ach = steps_per_launch / 32.0 * slots / (kernel_ms * 1e-3)
-        pk = 148 * 4 * clocks["sm_mhz"] * 1e6
-        roofline["fp32_pipe"] = {"bound": "fp32 pipe issue", "achieved": ach, "peak": pk, "unit": "warp-instruction slots/s",
-                                 "frac": ach / pk, "slots_per_warp_step": slots,
-                                 "note": "peak = 148 SMs x 4 sub-partitions x sampled SM clock; slots from profiles/traffic.json"}
+
+def compact(m):
+    """sub-record of the JSON line from a gpu_measure() result"""
+    r = {k: m[k] for k in ("value", "ms_per_step", "rays_per_s", "rays_total", "kernel_ms", "phases_ms", "gpu_launches", "checks")}
+    r["unit"] = "ray-steps/s"
+    if m.get("e2e"):
+        r["e2e"] = {k: m["e2e"][k] for k in ("value", "ms_per_step", "phases_ms", "h2d_bytes_per_step", "d2h_bytes_per_step", "host_memory")}
+    return r
+
+
+def run_gpu_arm(args, wl):
+    import torch
+    from turbulence_tracing_b200 import distributed as ttd
+    from turbulence_tracing_b200 import particle_tracker as pt, ray_transfer_matrix as rtm, turboGen as tg
+    from turbulence_tracing_b200 import _lib
+
+    ctx = GpuCtx()
+    ctx.torch, ctx.ttd, ctx.pt, ctx.rtm, ctx.tg, ctx.lib = torch, ttd, pt, rtm, tg, _lib
+    ctx.rank, ctx.world, local = ttd.init_from_env()
+    rank, world = ctx.rank, ctx.world
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    ctx.dev = dev = torch.device("cuda", local)
+    numa = ttd.bind_to_gpu_numa_node(local) if hasattr(ttd, "bind_to_gpu_numa_node") else None
+    _lib.load(build_if_missing=False)
+    n_half, rays, desc = WORKLOADS[wl]
+    if args.rays:
+        rays = args.rays
+    dtype = args.dtype
+    cache = {}
+
+    # ---- the headline record: weak scaling, `rays` per GPU -----------------------------------------------------
+    first, _ = ttd.shard_range(rays * world, rank, world)
+    main = gpu_measure(ctx, args, wl, rays_per_rank=rays, first_ray=first, dtype=dtype, steps=args.steps, warmup=args.warmup,
+                       do_e2e=not args.no_e2e, sampler=ClockSampler(local), steps_per_cell=args.steps_per_cell,
+                       face_grid=not args.no_face_grid, pageable=(not args.no_e2e and not args.no_extras), ne_cache=cache,
+                       beam=args.beam or BEAM_SIZE)
+    M, aux, clocks = main["M"], main["aux"], main["clocks"]
+    faces = main["faces"]
+    key = f"{wl}/{dtype}/" + ("faces" if faces else str(args.variant or 3))
+    kern = TRACE_KERNELS.get((dtype, aux, faces), ("", "trace kernel"))
+    if faces:
+        bps, note = 48, "one cell face = 3 x 16 B of bilinear coefficients per ray-step (SURVEY 8d counted 4 stages x 8 corners x 16 B = 512 B for a per-stage gather)"
+    else:
+        bps = 64 * (2 if dtype == "float64" else 1) * (2 if aux else 1)
+        note = "4 corners of the next plane per ray-step, 16 B each in FP32 (32 B in FP64; x2 with the B/kappa grid)"
+    roofline = build_roofline(key, kern, main["steps_per_launch"], main["kernel_ms"], clocks, bps, note) if not args.rays else None
+
+    # ---- sub-records (same machinery, fewer steps): strong scaling, configs[4] share, configs[1], configs[3], FP64, ... ----
+    extra = {}
+    if not args.no_extras and wl == "c3" and not args.rays:
+        xs, xw = max(2, args.steps // 2), 2
+        if world > 1:
+            f0, cnt = ttd.shard_range(WORKLOADS["c3"][1], rank, world)
+            m = gpu_measure(ctx, args, "c3", rays_per_rank=cnt, first_ray=f0, dtype="float32", steps=xs, warmup=xw,
+                            do_e2e=not args.no_e2e, ne_cache=cache)
+            extra["strong_c3"] = dict(compact(m), scaling="strong",
+                                      workload=f"configs[2] strong scaling: 513^3 cube, 1e8 rays TOTAL sharded over {world} GPUs "
+                                               f"(example_MPI.py:117-149), histogram all-reduce")
+        if world == 1:
+            m = gpu_measure(ctx, args, "c3", rays_per_rank=rays, first_ray=0, dtype="float32", steps=xs, warmup=xw, do_e2e=False,
+                            ne_cache=cache, beam=EXTENT)
+            extra["wide_beam_c3"] = dict(compact(m), workload="configs[2] with beam_size = extent (example_multiprocess.py:46-50): "
+                                         "rays outside the cube's cross-section or leaving sideways take the general kernel",
+                                         deferred_fraction=1.0 - m["checks"]["status_exit_face"] / m["checks"]["rays"])
+            m = gpu_measure(ctx, args, "c3", rays_per_rank=rays, first_ray=0, dtype="float32", steps=xs, warmup=xw, do_e2e=False,
+                            ne_cache=cache, bin_scale=1)
+            extra["bin_scale_1_c3"] = dict(compact(m), workload="configs[2] with the detector at bin_scale=1 (2574 x 3448 bins, example_MPI.py:69)")
+            m = gpu_measure(ctx, args, "c3", rays_per_rank=rays, first_ray=0, dtype="float32", steps=xs, warmup=xw, do_e2e=False,
+                            ne_cache=cache, face_grid=False)
+            extra["corner_grid_c3"] = dict(compact(m), workload="configs[2] through tt_trace (float4 corner grid, round-1 path)")
+            for name, w, dt, spc in (("c2", "c2", "float32", 1), ("c2_fp64", "c2", "float64", 2), ("c4", "c4", "float32", 1)):
+                m = gpu_measure(ctx, args, w, rays_per_rank=WORKLOADS[w][1], first_ray=0, dtype=dt, steps=xs, warmup=xw,
+                                do_e2e=False, ne_cache=cache, steps_per_cell=spc)
+                extra[name] = dict(compact(m), workload=WORKLOADS[w][2] + f", {dt}, {spc} step(s) per cell")
+        if world in (1, 8):
+            per = WORKLOADS["c5"][1]
+            f0, _ = ttd.shard_range(per * world, rank, world)
+            main.pop("ne", None)
+            m = gpu_measure(ctx, args, "c5", rays_per_rank=per, first_ray=f0, dtype="float32", steps=2, warmup=1,
+                            do_e2e=(not args.no_e2e and world == 8), ne_cache=cache)
+            extra["c5"] = dict(compact(m), scaling="weak", workload=WORKLOADS["c5"][2] +
+                               (" -- all 8 shares: 1e9 rays" if world == 8 else " -- one GPU's share of the 8-GPU job"))
+    cache.clear()
+    main.pop("ne", None)
 
     # ---- CPU baseline on a bounded sample of the same cube (rank 0, N = 1 only) ----------------------
     cpu = cpu_c = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             # a fresh process (no CUDA context to fork) runs the CPU path on the very same cube
+            n_half = WORKLOADS[wl][0]
+            f = tg.gaussian3D_FFT(n_half, SPECTRUM, seed=1234, dtype="float32", return_device=True).torch
             path = f"/tmp/tt_ne_{os.getpid()}.npy"
-            np.save(path, ne.cpu().numpy())
+            np.save(path, ne_from_field(f, torch).cpu().numpy())
+            del f
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", wl,
                                   "--cube-file", path, "--steps", "1", "--warmup", "0", "--cpu-rays",
                                   str(args.cpu_rays)], capture_output=True, text=True, timeout=1500)
@@ -510,26 +669,32 @@ def run_gpu_arm(args, wl):
             ref_line = json.loads(out.stdout.strip().splitlines()[-1])
             cpu, cpu_c = ref_line["cpu_baseline"], ref_line.get("cpu_baseline_c")
         except Exception as e:      # reported, never silently dropped
-            cpu = {"value": None, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": None, "unit": "ray-steps/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"failed: {type(e).__name__}: {e}"}
 
     if rank == 0:
+        e2e = main["e2e"]
         line = {
-            "metric": "ray-steps/s", "value": value, "unit": "ray-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "ray-steps/s", "value": main["value"], "unit": "ray-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
-            "rays_per_s": rays_per_s,
+            "rays_per_s": main["rays_per_s"], "host_cores": os.cpu_count(),
             "config": {"workload": desc, "cube": f"{M}^3", "rays_per_gpu": rays, "steps_per_cell": args.steps_per_cell,
-                       "beam_size_m": BEAM_SIZE, "divergence_rad": DIVERGENCE, "detector": "Shadowgraphy bin_scale=10",
+                       "beam_size_m": args.beam or BEAM_SIZE, "divergence_rad": DIVERGENCE, "detector": "Shadowgraphy bin_scale=10",
                        "parallelism": f"rays sharded x{world}, cube replicated (NCCL broadcast), histogram all-reduce",
-                       "l2": "inputs larger than L2 (gradient grid %.2f GB, rays %.2f GB)" % (
-                           M**3 * (16 if dtype == "float32" else 32) / 1e9, rays * 48 / 1e9),
-                       "cube_setup_s": t_cube, "kernel_variant": args.variant},
-            "e2e": e2e, "gpu_launches": 5 * args.steps * world,
-            "gpu_launches_note": "per step and GPU: calc_dndr_kernel, morton_key_kernel, trace_event_kernel_f32x2, trace_kernel "
-                                 "(second pass over deferred rays), optics_hist_kernel (+ 6 CUB radix-sort kernels)",
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "clocks": clocks, "phases_ms": phases,
-            "histogram_sum": int(H_dev.sum().item()),
+                       "trace_path": "face-coefficient grid (tt_build_face_grid + tt_trace_faces)" if faces else "float4 corner grid (tt_trace)",
+                       "l2": "inputs larger than L2 (gradient grid %.2f GB%s, rays %.2f GB)" % (
+                           M**3 * (16 if dtype == "float32" else 32) / 1e9,
+                           (" + face-coefficient grid %.2f GB" % ((M - 1) ** 2 * (M + 1) * 48 / 1e9)) if faces else "", rays * 48 / 1e9),
+                       "cube_setup_s": main["cube_setup_s"], "kernel_variant": args.variant, "numa_binding": numa},
+            "e2e": e2e, "e2e_pageable": main.get("e2e_pageable"),
+            "gpu_launches": main["gpu_launches"],
+            "gpu_launches_note": "counted by the library (tt_launch_count: every <<<>>> of its own kernels) over the timed region, all ranks; "
+                                 "per step and GPU: calc_dndr_kernel, face_grid_kernel, morton_key_kernel, trace_face_kernel_f32x2, "
+                                 "trace_kernel (second pass over deferred rays, returns at once when there are none), optics_hist_kernel "
+                                 "(CUB's radix-sort passes are library kernels and not counted)",
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_c": cpu_c, "clocks": clocks, "phases_ms": main["phases_ms"],
+            "checks": main["checks"], "histogram_sum": main["checks"]["histogram_sum"], "extra": extra,
         }
         emit(line)
     if world > 1:
@@ -576,6 +741,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-face-grid", action="store_true", help="trace over the float4 corner grid (tt_trace) instead of the face-coefficient grid")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (strong scaling, configs[1]/[3]/[4], FP64, wide beam, bin_scale=1, pageable e2e)")
+    ap.add_argument("--beam", type=float, default=0.0, help="beam radius in m (default 4e-3)")
     ap.add_argument("--cpu-port", action="store_true", help="(reference arm) time the numpy/scipy restatement instead of the reference's own modules")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

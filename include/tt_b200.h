@@ -9,11 +9,12 @@
  * Conventions
  *   - plain pointers and sizes only; every *_dev pointer is DEVICE memory owned by the caller,
  *     every other pointer is HOST memory.  The library allocates nothing persistent: scratch
- *     space is passed in after a *_workspace() size query.  One exception, 4 bytes: tt_trace /
- *     tt_trace_aux / tt_trace_axes take a stream-ordered flag word ("did the first pass defer a
- *     ray?") from the device's default memory pool (cudaMallocAsync / cudaFreeAsync on `stream`)
- *     and, on first use, set that pool's release threshold so that it keeps its memory across
- *     synchronisations -- without it the allocation costs milliseconds per launch.
+ *     space is passed in after a *_workspace() size query.  One exception: tt_trace / tt_trace_faces /
+ *     tt_trace_aux / tt_trace_axes take stream-ordered scratch (cudaMallocFromPoolAsync / cudaFreeAsync on
+ *     `stream`) from a memory pool OWNED by the library, which keeps what it was given across
+ *     synchronisations (a fresh allocation costs milliseconds per launch): 8 bytes of flag words ("did the
+ *     first pass defer a ray?", how many) and, for tt_trace / tt_trace_faces, a list of the deferred ray ids
+ *     (4 bytes per ray of the launch, at most 64 MB).
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); entry points that return
  *     device results do not synchronise.  The *_host convenience entry points (host buffers
  *     in and out) synchronise before returning.
@@ -125,9 +126,10 @@ int tt_trace(const tt_trace_params* p, const void* grid4_dev, const double* s0_d
  * Same reference function as tt_trace (particle_tracker.py:312-331 solve, :398-419 dsdt, :333-380 ray_at_exit), same
  * arguments, outputs, status flags and ray order; the trilinear look-up of dsdt (:243-256) reads a second, derived
  * grid: per cell FACE (iw, cell row, cell column) the bilinear coefficients (A, B, C, D) of the three gradient
- * components, g(tu, tv) = A + tu B + tv (C + tu D), with the step-size factors folded in -- three 16-byte words
+ * components, g(tu, tv) = A + tu B + tv (C + tu D) in cell coordinates tu, tv in [-1/2, 1/2], with the step-size
+ * factors folded in -- three 16-byte words
  *   (A_u, A_v, B_u, B_v) (C_u, C_v, D_u, D_v) (A_w, C_w, B_w, D_w),   scaled by h_w^2/h_u, h_w^2/h_v, h_w
- * = 48 (nu-1)(nv-1) nw bytes (tt_face_grid_bytes), formed ONCE per calc_dndr by tt_build_face_grid from the float4
+ * = 48 (nu-1)(nv-1)(nw+1) bytes (tt_face_grid_bytes; the last plane is a spare copy), formed ONCE per calc_dndr by tt_build_face_grid from the float4
  * grid of tt_calc_dndr instead of once per ray and plane inside the trace kernel.  tt_trace_faces marches every ray
  * over it (one RK4 step per cell, steps ending on cell faces as in tt_trace variant 3) and hands unusual rays (outside
  * / steep / side exit / time cap / non-finite) to the same general kernel over grid4_dev.  status_dev is required.

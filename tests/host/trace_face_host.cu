@@ -18,7 +18,7 @@ static void fill(tt::TraceArgs& A, const int n_xyz[3], const double origin_xyz[3
     A.extent = extent; A.s_max = s_max; A.spc = 1; A.np = np;
 }
 
-// faces: 48 (nu-1)(nv-1) nw bytes, as tt_build_face_grid writes them
+// faces: 48 (nu-1)(nv-1)(nw+1) bytes, as tt_build_face_grid writes them (the last plane repeats face nw-1)
 extern "C" int host_build_face_grid(const void* grid4, const int n_xyz[3], const double spacing_xyz[3], int par, void* faces) {
     using namespace tt;
     const Frame f = frame_of(par);
@@ -29,9 +29,10 @@ extern "C" int host_build_face_grid(const void* grid4, const int n_xyz[3], const
     face_scales(h, su, sv, sw);
     const long long plane = (long long)n[0] * n[1];
     float4* out = (float4*)faces;
-    for (int k = 0; k < n[2]; ++k)
+    for (int kk = 0; kk <= n[2]; ++kk)
         for (int cv = 0; cv < n[1] - 1; ++cv)
             for (int cu = 0; cu < n[0] - 1; ++cu) {
+                const int k = kk < n[2] ? kk : n[2] - 1;
                 face_grid_cell((const float4*)grid4, n[0], plane, cu, cv, k, su, sv, sw, out);
                 out += 3;
             }

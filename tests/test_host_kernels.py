@@ -924,7 +924,7 @@ def _run_faces(lib, G, x, y, z, par, extent, s0, want_sf=True, second_pass=True)
     org = (C.c_double * 3)(x[0], y[0], z[0])
     h = (C.c_double * 3)(*[(a[-1] - a[0]) / (len(a) - 1) for a in (x, y, z)])
     nw, nv, nu = G.shape[:3]
-    faces = np.full((nw, nv - 1, nu - 1, 12), np.nan, dtype=np.float32)
+    faces = np.full((nw + 1, nv - 1, nu - 1, 12), np.nan, dtype=np.float32)
     assert lib.host_build_face_grid(p(G), C.byref(dims), C.byref(h), par, p(faces)) == 0
     assert np.isfinite(faces).all()
     rc = lib.host_trace_faces(p(G), p(faces), C.byref(dims), C.byref(org), C.byref(h), par, float(extent),
@@ -935,8 +935,8 @@ def _run_faces(lib, G, x, y, z, par, extent, s0, want_sf=True, second_pass=True)
 
 
 def test_face_grid_builder_source(face_lib):
-    """face_grid_cell: (A, B, C, D) of every cell face = FP64 differences of the float4 node grid times the folded
-    step-size factors, in the word order the kernel loads"""
+    """face_grid_cell: (A, B, C, D) of every cell face (bilinear form in centred cell coordinates) = FP64 sums and
+    differences of the float4 node grid times the folded step-size factors, in the word order the kernel loads"""
     rng = np.random.default_rng(3)
     xx, yy, zz = np.linspace(-5e-3, 5e-3, 9), np.linspace(-4e-3, 4e-3, 7), np.linspace(-5e-3, 5e-3, 6)
     for par in (0, 1, 2):
@@ -950,7 +950,10 @@ def test_face_grid_builder_source(face_lib):
         sc = [float(np.float32(hw / hu)) * hw, float(np.float32(hw / hv)) * hw, hw]
         g = G.astype(np.float64)
         c00, c10, c01, c11 = g[:, :-1, :-1], g[:, :-1, 1:], g[:, 1:, :-1], g[:, 1:, 1:]
-        A, B, Cc, D = c00, c10 - c00, c01 - c00, ((c11 - c01) - c10) + c00
+        A, B = 0.25 * ((c00 + c10) + (c01 + c11)), 0.5 * ((c10 - c00) + (c11 - c01))      # centred cell coordinates
+        Cc, D = 0.5 * ((c01 - c00) + (c11 - c10)), ((c11 - c01) - c10) + c00
+        np.testing.assert_array_equal(faces[-1], faces[-2])                                # the spare plane
+        faces = faces[:-1]
         want = np.empty(faces.shape)
         for m, s in enumerate(sc[:2]):
             want[..., 0 + m], want[..., 2 + m], want[..., 4 + m], want[..., 6 + m] = s * A[..., m], s * B[..., m], s * Cc[..., m], s * D[..., m]

@@ -88,6 +88,11 @@ PROTOTYPES = {
 _lib = None
 
 
+def lib_path() -> str:
+    """path of the shared library load() uses (TT_B200_LIB overrides the in-tree build)"""
+    return LIB_PATH
+
+
 def load(build_if_missing: bool = True):
     """Load libtt_b200.so (building it with nvcc when absent).  Raises TTError otherwise."""
     global _lib

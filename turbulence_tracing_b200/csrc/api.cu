@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 // default pool right after a synchronisation costs 0.7-15 ms on a B200 VM (the pool hands its memory back to the
 // driver at every sync, profiles/r01_diag_mallocasync.txt), and changing the default pool's threshold would change
 // the behaviour of every other cudaMallocAsync user in the host process.
-unsigned int* scratch_flag(cudaStream_t s) {
+void* scratch_alloc(size_t bytes, cudaStream_t s) {
     static std::mutex mu;
     static cudaMemPool_t pools[64] = {};
     static bool tried[64] = {};
@@ -51,14 +51,19 @@ unsigned int* scratch_flag(cudaStream_t s) {
         }
         pool = pools[dev];
     }
-    unsigned int* flag = nullptr;
-    const cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&flag, sizeof(unsigned int), pool, s)
-                               : cudaMallocAsync((void**)&flag, sizeof(unsigned int), s);
+    void* ptr = nullptr;
+    const cudaError_t e = pool ? cudaMallocFromPoolAsync(&ptr, bytes, pool, s) : cudaMallocAsync(&ptr, bytes, s);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return nullptr;
     }
-    cudaMemsetAsync(flag, 0, sizeof(unsigned int), s);
+    return ptr;
+}
+
+// two zeroed words: [0] "did the first pass defer a ray?", [1] number of deferred rays found by the compaction
+unsigned int* scratch_flag(cudaStream_t s) {
+    unsigned int* flag = (unsigned int*)scratch_alloc(2 * sizeof(unsigned int), s);
+    if (flag) cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned int), s);
     return flag;
 }
 

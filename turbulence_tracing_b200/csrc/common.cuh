@@ -32,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // its memory back to the driver at every synchronisation, and the next cudaMallocAsync has to map fresh physical
 // memory -- milliseconds up to (measured on a B200 VM) hundreds of milliseconds per trace launch.
 unsigned int* scratch_flag(cudaStream_t s);
+void* scratch_alloc(size_t bytes, cudaStream_t s);       // stream-ordered scratch from the same pool (nullptr on failure)
 
 void count_launch();             // api.cu: process-wide counter behind tt_launch_count()
 inline int launch_check(const char* name) {

@@ -24,6 +24,8 @@ struct TraceArgs {
     // multiplies, no double->float conversions)
     long long plane_elems;   // nu * nv
     float hwf, ruf, rvf;     // (float) h_w, h_w/h_u, h_w/h_v
+    unsigned int list_cap;        // second pass: capacity of the compacted list of deferred rays (0: no list); the flag-scan
+                                  // kernel then only runs when more rays than that were deferred (any_deferred[1] > list_cap)
     unsigned int* any_deferred;   // device flag (nullable): set by an event kernel that deferred a ray, so
                                   // that the second pass can return at once when there is nothing to do
 };

@@ -19,11 +19,13 @@ face_grid_kernel(const float4* __restrict__ grid, float4* __restrict__ faces, in
                  double sw) {
     const int nuc = nu - 1, nvc = nv - 1;
     const long long plane = (long long)nu * nv;
-    const long long total = (long long)nuc * nvc * nw;
+    const long long total = (long long)nuc * nvc * (nw + 1);        // + the spare plane: face nw-1 once more
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int cu = (int)(i % nuc);
         const long long r = i / nuc;
-        const int cv = (int)(r % nvc), k = (int)(r / nvc);
+        const int cv = (int)(r % nvc);
+        int k = (int)(r / nvc);
+        if (k > nw - 1) k = nw - 1;
         float4 out[3];
         face_grid_cell(grid, nu, plane, cu, cv, k, su, sv, sw, out);
         float4* o = faces + 3 * i;
@@ -68,7 +70,8 @@ int launch_trace_face(const void* faces, const double* s0, const uint32_t* perm,
 extern "C" size_t tt_face_grid_bytes(const int n_xyz[3], int par) {
     if (!n_xyz || par < 0 || par > 2 || n_xyz[0] < 2 || n_xyz[1] < 2 || n_xyz[2] < 2) return 0;
     const tt::Frame f = tt::frame_of(par);
-    return 48ull * (size_t)(n_xyz[f.a[0]] - 1) * (size_t)(n_xyz[f.a[1]] - 1) * (size_t)n_xyz[f.a[2]];
+    // nw faces + one spare plane (the kernel prefetches two planes ahead without a bounds test)
+    return 48ull * (size_t)(n_xyz[f.a[0]] - 1) * (size_t)(n_xyz[f.a[1]] - 1) * ((size_t)n_xyz[f.a[2]] + 1);
 }
 
 extern "C" int tt_build_face_grid(const void* grid4_dev, const int n_xyz[3], const double spacing_xyz[3], int par,
@@ -86,7 +89,7 @@ extern "C" int tt_build_face_grid(const void* grid4_dev, const int n_xyz[3], con
     }
     double su, sv, sw;
     face_scales(h, su, sv, sw);
-    const long long total = (long long)(n[0] - 1) * (n[1] - 1) * n[2];
+    const long long total = (long long)(n[0] - 1) * (n[1] - 1) * (n[2] + 1);
     const int block = 256;
     long long blocks = (total + block - 1) / block;
     if (blocks > 148LL * 64) blocks = 148LL * 64;

@@ -7,6 +7,9 @@
 // words per face cell, in the register-pair order the packed arithmetic wants:
 //      word 0 = (A_u, A_v, B_u, B_v)      word 1 = (C_u, C_v, D_u, D_v)      word 2 = (A_w, C_w, B_w, D_w)
 //      g_m(tu, tv) = A_m + tu B_m + tv (C_m + tu D_m)          on face k of the cell column (cu, cv)
+// in CENTRED cell coordinates tu, tv in [-1/2, 1/2] (A = mean of the 4 corners, ...): the test "does the predicted end
+// of the step lie outside the cell" is then |tu| > 1/2 || |tv| > 1/2, two compares with free |.| operand modifiers
+// instead of four, and the polynomial is evaluated around the middle of the cell.
 // with the step-size factors folded in (index-space march, independent variable = the w-fraction):
 //      (A..D)_u = (h_w^2 / h_u) g_u,   (A..D)_v = (h_w^2 / h_v) g_v,   (A..D)_w = h_w g_w,    g = grad(ne/nc) * (-1/2)
 // so that with the SCALED direction  e = (d_u h_w/h_u, d_v h_w/h_v, d_w)  the ray equations per unit w-fraction are
@@ -45,9 +48,11 @@ TT_HD void face_grid_cell(const float4* __restrict__ grid, int nu, long long pla
                           double sv, double sw, float4* __restrict__ out) {
     const float4* p = grid + ((size_t)k * plane + (size_t)cv * nu + cu);
     const float4 c00 = GridT<float>::ld(p), c10 = GridT<float>::ld(p + 1), c01 = GridT<float>::ld(p + nu), c11 = GridT<float>::ld(p + nu + 1);
-#define TT_FC(m, s, a, b, c, d)                                                                   \
-    const float a = (float)(s * (double)c00.m), b = (float)(s * ((double)c10.m - (double)c00.m)), \
-                c = (float)(s * ((double)c01.m - (double)c00.m)),                                 \
+    // centred: A = mean of the corners, B = mean u-difference, C = mean v-difference, D = the mixed difference
+#define TT_FC(m, s, a, b, c, d)                                                                                          \
+    const float a = (float)(s * (0.25 * (((double)c00.m + (double)c10.m) + ((double)c01.m + (double)c11.m)))),           \
+                b = (float)(s * (0.5 * (((double)c10.m - (double)c00.m) + ((double)c11.m - (double)c01.m)))),            \
+                c = (float)(s * (0.5 * (((double)c01.m - (double)c00.m) + ((double)c11.m - (double)c10.m)))),            \
                 d = (float)(s * ((((double)c11.m - (double)c01.m) - (double)c10.m) + (double)c00.m));
     TT_FC(x, su, au, bu, cu_, du)
     TT_FC(y, sv, av, bv, cv_, dv)
@@ -118,46 +123,51 @@ TT_HD void face_eval(const FaceQ& q, f32x2 tuv, f32x2& guv, float& gw) {
                                // base + primed/2 and the far face (which IS the next base): 12 packed operations less
 #endif
 
-// One RK4 step of the ray inside its cell, from w-fraction fw over h (FULL: fw = 0, h = 1 for every lane).
-// In: base / primed polynomial, state (tuv, duv, dw); out: the new state; FULL: B becomes the far face (in place: the
-// base face is dead once the mid-step coefficients exist, and the far face is the next cell's base).
+// One RK4 step of the ray inside its cell, from w-fraction fw over h (FULL: fw = 0 and h = 1 for every lane of the warp).
+// In: base / primed polynomial, state (tuv, duv, dw), stage-1 slopes; out: the new state; FULL: B becomes the far face
+// (in place: the base face is dead once the mid-step coefficients exist, and the far face is the next cell's base).
+//
+// A ray's bits must not depend on which of the two instantiations its warp happened to take (a chunked solve and a
+// single launch sort the rays into different warps).  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// in spite of the explicit rounding modifiers (and folds an fma2 by a literal 1 into that), so the step is written in
+// already-fused form -- no packed product is ever the operand of a packed addition -- and h stays a run-time value in
+// both instantiations; what differs is only how the stage coefficients are obtained, and those agree exactly
+// (fma(0, P, B) = B, fma(1, P, B) = rn(B + P)).  Tested on the device: sorted == unsorted == chunked, bit for bit.
 template <bool FULL, bool TRACK_S>
 TT_HD bool face_step(FaceQ& B, const FaceQ& P, f32x2& tuv, f32x2& duv, float& dw, float& s, float fw, float h,
-                     float q, f32x2 aUV, f32x2 aduv, float adw) {
-    const float half = FULL ? 0.5f : 0.5f * h;
-    const f32x2 HALF = bc2(half), H = bc2(FULL ? 1.f : h);
+                     float q1, f32x2 aUV, f32x2 aduv, float adw) {
+    const float half = 0.5f * h;
+    const f32x2 HALF = bc2(half), H = bc2(h);
     // ---- stages 2 and 3 share their w-fraction ------------------------------------------------------------
     f32x2 suv = fma2(HALF, aUV, tuv), duv2 = fma2(HALF, aduv, duv);
     float dw2 = fmaf(half, adw, dw);
-    const float q1 = q;
-    q = trcp<float>(dw2);
+    const float q2 = trcp<float>(dw2);
     bool ok = dw2 > 0.f;
     const FaceQ M = face_at(B, P, bc2(FULL ? 0.5f : fw + half));
-    const f32x2 bUV = mul2(duv2, bc2(q));
+    const f32x2 bUV = mul2(duv2, bc2(q2));
     f32x2 g; float gw;
     face_eval(M, suv, g, gw);
-    const f32x2 bduv = mul2(g, bc2(q));
-    const float bdw = gw * q, q2 = q;
+    const f32x2 bduv = mul2(g, bc2(q2));
+    const float bdw = gw * q2;
     suv = fma2(HALF, bUV, tuv); duv2 = fma2(HALF, bduv, duv); dw2 = fmaf(half, bdw, dw);
-    q = trcp<float>(dw2); ok = ok && dw2 > 0.f;
-    const f32x2 cUV = mul2(duv2, bc2(q));
+    const float q3 = trcp<float>(dw2);
+    ok = ok && dw2 > 0.f;
+    const f32x2 Q3 = bc2(q3), cUV = mul2(duv2, Q3), sUV = fma2(duv2, Q3, bUV);              // sUV = b + c
     face_eval(M, suv, g, gw);
-    const f32x2 cduv = mul2(g, bc2(q));
-    const float cdw = gw * q, q3 = q;
+    const f32x2 cduv = mul2(g, Q3), sduv = fma2(g, Q3, bduv);
+    const float cdw = gw * q3, sdw = fmaf(gw, q3, bdw);
     // ---- stage 4 at the end of the step -------------------------------------------------------------------
-    suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = FULL ? dw + cdw : fmaf(h, cdw, dw);
-    q = trcp<float>(dw2); ok = ok && dw2 > 0.f;
-    const f32x2 eUV = mul2(duv2, bc2(q));
+    suv = fma2(H, cUV, tuv); duv2 = fma2(H, cduv, duv); dw2 = fmaf(h, cdw, dw);
+    const float q4 = trcp<float>(dw2);
+    ok = ok && dw2 > 0.f;
     if (FULL) { B = face_add(B, P); face_eval(B, suv, g, gw); }
     else face_eval(face_at(B, P, bc2(fw + h)), suv, g, gw);
-    const f32x2 eduv = mul2(g, bc2(q));
-    const float edw = gw * q;
-    const float h6 = FULL ? (float)(1.0 / 6.0) : h * (float)(1.0 / 6.0);
-    const f32x2 H6 = bc2(h6), TWO = bc2(2.f);
-    tuv = fma2(H6, add2(add2(aUV, mul2(TWO, add2(bUV, cUV))), eUV), tuv);
-    duv = fma2(H6, add2(add2(aduv, mul2(TWO, add2(bduv, cduv))), eduv), duv);
-    dw = fmaf(h6, adw + 2.f * (bdw + cdw) + edw, dw);
-    if (TRACK_S) s = fmaf(h6, q1 + 2.f * (q2 + q3) + q, s);
+    const float h6 = h * (float)(1.0 / 6.0);
+    const f32x2 H6 = bc2(h6), TWO = bc2(2.f), Q4 = bc2(q4);
+    tuv = fma2(H6, fma2(duv2, Q4, fma2(TWO, sUV, aUV)), tuv);                                // a + 2 (b + c) + e
+    duv = fma2(H6, fma2(g, Q4, fma2(TWO, sduv, aduv)), duv);
+    dw = fmaf(h6, fmaf(gw, q4, fmaf(2.f, sdw, adw)), dw);
+    if (TRACK_S) s = fmaf(h6, q4 + fmaf(2.f, q2 + q3, q1), s);
     return ok;
 }
 
@@ -193,8 +203,8 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
     float tu0 = 0.f, tv0 = 0.f, fw = 0.f;
     if (fast) {
         double fl;
-        fl = fmin(floor(X[0]), (double)(nu - 2)); cu = (int)fl; tu0 = (float)(X[0] - fl);
-        fl = fmin(floor(X[1]), (double)(nv - 2)); cv = (int)fl; tv0 = (float)(X[1] - fl);
+        fl = fmin(floor(X[0]), (double)(nu - 2)); cu = (int)fl; tu0 = (float)((X[0] - fl) - 0.5);     // centred
+        fl = fmin(floor(X[1]), (double)(nv - 2)); cv = (int)fl; tv0 = (float)((X[1] - fl) - 0.5);
         fl = floor(X[2]); k = (int)fl; fw = (float)(X[2] - fl);
     }
     f32x2 tuv = pk2(tu0, tv0), duv = pk2((float)D[0] * FA.ruf, (float)D[1] * FA.rvf);     // scaled transverse direction
@@ -207,23 +217,23 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
         FaceW N;
         P = face_sub(face_ld(p + fplane), B);
         while (true) {
-            // face k+2, consumed at the end of the step (in the last cell: face k+1 once more, never used -- an
-            // unconditional load goes straight into N's registers, a predicated one through temporaries and 12 moves)
-            N = face_ldw(p + (k + 2 <= nw - 1 ? 2 * fplane : fplane));
+            // face k+2, consumed at the end of the step.  Unconditional (a predicated load goes through temporaries and
+            // 12 moves): the grid carries one spare plane behind the last face for the load issued in the last cell
+            N = face_ldw(p + 2 * fplane);
             // ---- stage 1 and the length of this step -------------------------------------------------------
-            const float q = trcp<float>(dw);
-            bool ok = dw > (float)TT_MARCH_MIN_DW;
+            const float q = trcp<float>(dw);        // (dw > TT_MARCH_MIN_DW: checked at the entry and after every step)
+            bool ok = true;
             const f32x2 aUV = mul2(duv, bc2(q));
             float h = 1.f - fw;
             int cross = 0;
             {
                 const f32x2 puv = fma2(bc2(h), aUV, tuv);
                 const float pu = lo2(puv), pv = hi2(puv);
-                if (pu > 1.f || pu < 0.f || pv > 1.f || pv < 0.f) {
+                if (fabsf(pu) > 0.5f || fabsf(pv) > 0.5f) {
                     const float aU = lo2(aUV), aV = hi2(aUV), tu = lo2(tuv), tv = hi2(tuv);
                     float lu = 2.f, lv = 2.f;
-                    if (aU > 0.f) lu = chord_fraction<float>(1.f - tu, h * aU); else if (aU < 0.f) lu = chord_fraction<float>(-tu, h * aU);
-                    if (aV > 0.f) lv = chord_fraction<float>(1.f - tv, h * aV); else if (aV < 0.f) lv = chord_fraction<float>(-tv, h * aV);
+                    if (aU > 0.f) lu = chord_fraction<float>(0.5f - tu, h * aU); else if (aU < 0.f) lu = chord_fraction<float>(-0.5f - tu, h * aU);
+                    if (aV > 0.f) lv = chord_fraction<float>(0.5f - tv, h * aV); else if (aV < 0.f) lv = chord_fraction<float>(-0.5f - tv, h * aV);
                     const float lam = fminf(lu, lv);
                     if (lam < 1.f) {
                         cross = lu <= lv ? (aU > 0.f ? 1 : -1) : (aV > 0.f ? 2 : -2);
@@ -240,7 +250,7 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
 #endif
             if (full) {
                 face_eval(B, tuv, g, gw);
-                ok = face_step<true, TRACK_S>(B, P, tuv, duv, dw, s, 0.f, 1.f, q, aUV, mul2(g, bc2(q)), gw * q) && ok;
+                ok = face_step<true, TRACK_S>(B, P, tuv, duv, dw, s, 0.f, h, q, aUV, mul2(g, bc2(q)), gw * q) && ok;
                 if (!(ok && dw > (float)TT_MARCH_MIN_DW)) { fast = false; break; }
                 ++steps;
                 if (++k >= nw - 1) break;
@@ -277,8 +287,8 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
         deferred = true;
         steps = 0;
     } else {
-        const double Pu = A.o[0] + ((double)cu + (double)lo2(tuv)) * A.h[0];
-        const double Pv = A.o[1] + ((double)cv + (double)hi2(tuv)) * A.h[1];
+        const double Pu = A.o[0] + (((double)cu + 0.5) + (double)lo2(tuv)) * A.h[0];
+        const double Pv = A.o[1] + (((double)cv + 0.5) + (double)hi2(tuv)) * A.h[1];
         const double Pw = A.o[2] + (double)(nw - 1) * A.h[2];
         const double Vu = (double)lo2(duv) * FA.inv_ru * kC, Vv = (double)hi2(duv) * FA.inv_rv * kC, Vw = (double)dw * kC;
         const double tb = (Pw - A.extent) / Vw;
