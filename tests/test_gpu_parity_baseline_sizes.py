@@ -325,7 +325,7 @@ def test_face_coefficient_kernel_against_corner_grid_kernel_and_abi(tt):
     print(f"face-coefficient kernel vs corner-grid kernel, 257^3, 2e6 rays: {d:.1e} m = {d / PIXEL_M:.1e} pixel, angles {da:.1e} rad")
     assert d <= 2e-4 * PIXEL_M and da <= 2e-7            # FP32 rounding of two evaluation orders
     # (sf: the position along the beam at time T carries the FP32 sum of 256 path-time increments)
-    assert float((a[1][:3] - b[1][:3]).abs().max()) <= 1e-7 and float((a[1][3:] - b[1][3:]).abs().max()) <= 1e-6 * orc.C_LIGHT
+    assert float((a[1][:3] - b[1][:3]).abs().max()) <= 1e-7 and float((a[1][3:] - b[1][3:]).abs().max()) <= 3e-6 * orc.C_LIGHT
     assert torch.equal(a[3], b[3])                      # same rays marched / handed over / missed
     assert 0 < int((a[3] != 1).sum()) < 200_000 and a[4] == b[4] or abs(a[4] - b[4]) <= 1e-4 * b[4]
     m = torch.isfinite(b[2]).all(dim=0)

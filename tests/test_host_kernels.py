@@ -982,7 +982,9 @@ def test_face_kernel_body_on_the_host(face_lib, packed_lib):
     assert p <= 1e-3 * 52.3e-6 and d <= 2e-4 * 52.3e-6
     # sf (state at time T) and the no-sf instantiation
     sfd = np.abs(a[1] - b[1])
-    assert sfd[:3].max() <= 1e-8 and sfd[3:].max() <= 1e-6 * C_LIGHT
+    # (the position along the beam at time T carries the FP32 sum of the path-time increments; e_w ~ 1 is rounded at
+    # ulp(1) = 6e-8 once per step)
+    assert sfd[:3].max() <= 1e-7 and sfd[3:].max() <= 3e-6 * C_LIGHT
     a2 = _run_faces(face_lib, G, x, x, x, 2, 5e-3, s0, want_sf=False)
     np.testing.assert_array_equal(a2[0], a[0])
 
