@@ -556,7 +556,8 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
                  "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
                  "d2h_bytes_per_step": int(last2[0].numel() * 8 + 8), "gpu_launches": launches2,
                  "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
-                              "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None)},
+                              "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None),
+                              "chunk_growth": getattr(cube2, "last_pipeline_growth", None)},
                  "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
             del ne_host, s0_host, cube2
             return r
