@@ -148,8 +148,23 @@ extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const do
     p.s_max = 2.8284271247461903 * extent;   // sqrt(8) * extent (particle_tracker.py:317)
     p.steps_per_cell = steps_per_cell;
     p.dtype = dtype;
-    rc = tt_trace(&p, grid.p, (const double*)s0.p, np, (const uint32_t*)perm.p, (double*)rf.p, (double*)sf.p,
-                  (unsigned long long*)cnt.p, (uint8_t*)status.p, s);
+    // FP32 at one step per cell: the production path over the face-coefficient grid when it fits (as ElectronCube.solve)
+    DevBuf faces;
+    const size_t face_bytes = (dtype == TT_F32 && steps_per_cell == 1) ? tt_face_grid_bytes(n_xyz, par) : 0;
+    if (face_bytes) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && face_bytes + (1ull << 30) < free_b && faces.alloc(face_bytes) != cudaSuccess)
+            (void)cudaGetLastError();
+    }
+    if (faces.p) {
+        rc = tt_build_face_grid(grid.p, n_xyz, spacing_xyz, par, faces.p, s);
+        if (rc) return rc;
+        rc = tt_trace_faces(&p, grid.p, faces.p, (const double*)s0.p, np, (const uint32_t*)perm.p, (double*)rf.p, (double*)sf.p,
+                            (unsigned long long*)cnt.p, (uint8_t*)status.p, s);
+    } else {
+        rc = tt_trace(&p, grid.p, (const double*)s0.p, np, (const uint32_t*)perm.p, (double*)rf.p, (double*)sf.p,
+                      (unsigned long long*)cnt.p, (uint8_t*)status.p, s);
+    }
     if (rc) return rc;
     TT_CUDA(cudaMemcpyAsync(rf_host, rf.p, (size_t)np * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (sf_host) TT_CUDA(cudaMemcpyAsync(sf_host, sf.p, (size_t)np * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
