@@ -1,5 +1,6 @@
 """Simulation-cube loaders (turbulence_tracing_b200/io.py): VTK XML ImageData without the vtk package.  CPU only."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -88,3 +89,17 @@ def test_load_cube_npy_npz_and_errors(tmp_path):
     tio.write_vti(tmp_path / "ok.vti", a)
     with pytest.raises(tio.VTKFormatError):
         tio.read_vti(tmp_path / "ok.vti", array="missing")
+
+
+def test_pvti_readin_of_a_hand_written_vtk_file():
+    """tests/golden/vtk_handwritten/: a .pvti with two .vti pieces written by hand to the VTK XML format (legacy-style
+    headers: version 0.1, UInt32 block header; one piece ascii, one inline base64), NOT by this package's writers.
+    Cell data 4 x 3 x 2, value(i, j, k) = 100 i + 10 j + k + 0.5, x fastest -- what vtkXMLPImageDataReader +
+    vtk_to_numpy(...).reshape(order="F") of the reference's helper returns (example_kitchensink.py:7-36)."""
+    from turbulence_tracing_b200 import io as tio
+    path = os.path.join(os.path.dirname(__file__), "golden", "vtk_handwritten", "cube.pvti")
+    img, dim, spacing = tio.pvti_readin(path)
+    assert tuple(dim) == (4, 3, 2) and img.shape == (4, 3, 2)
+    i, j, k = np.meshgrid(np.arange(4), np.arange(3), np.arange(2), indexing="ij")
+    np.testing.assert_array_equal(img, (100.0 * i + 10.0 * j + k + 0.5).astype(np.float32))
+    np.testing.assert_allclose(spacing, [5e-5, 5e-5, 1e-4])
