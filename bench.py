@@ -529,7 +529,10 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
             def step_e2e():
                 marks = []
                 mark(marks)
-                cube2.external_ne(ne_np)                # host numpy -> H2D inside calc_dndr
+                if world > 1:                           # each rank uploads 1/world of the cube, one all-gather over NVLink
+                    cube2.external_ne(ttd.upload_cube_sharded(ne_np, device=dev))
+                else:
+                    cube2.external_ne(ne_np)            # host numpy -> H2D inside calc_dndr
                 cube2.calc_dndr(LWL)
                 mark(marks)
                 cube2.s0 = s0_np                        # host numpy -> H2D inside solve
@@ -553,11 +556,12 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
                  "host_memory": "pinned (torch pin_memory)" if pinned else "pageable (plain numpy arrays, as a drop-in caller passes)",
                  "trace_launches_per_step": len(trace_ms) // max(steps_e, 1),
                  "trace_kernels_ms_per_step": float(np.sum(trace_ms)) / max(steps_e, 1),
-                 "h2d_bytes_per_step": int(ne_host.numel() * 4 + s0_host.numel() * 8),
+                 "h2d_bytes_per_step": int(-(-ne_host.numel() // world) * 4 + s0_host.numel() * 8),      # per rank
                  "d2h_bytes_per_step": int(last2[0].numel() * 8 + 8), "gpu_launches": launches2,
                  "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
                               "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None),
                               "chunk_growth": getattr(cube2, "last_pipeline_growth", None)},
+                 "cube_upload": "sharded: 1/N per rank over PCIe + one NCCL all-gather (distributed.upload_cube_sharded)" if world > 1 else "whole cube",
                  "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}
             del ne_host, s0_host, cube2
             return r

@@ -25,6 +25,17 @@ VARIANTS = {
     "mb4": ["-DTT_EVENT_MIN_BLOCKS=4"],
     "b96": ["-DTT_EVENT_BLOCK=96", "-DTT_EVENT_MIN_BLOCKS=7"],      # 21 warps / SM at 96 registers
 }
+# variants of the face-coefficient kernel (trace_face.cu, the production kernel since round 2): tags start with "f_"
+FACE_VARIANTS = {
+    "f_new": [],
+    "f_b64": ["-DTT_FACE_BLOCK=64", "-DTT_FACE_MIN_BLOCKS=10"],
+    "f_b96": ["-DTT_FACE_BLOCK=96", "-DTT_FACE_MIN_BLOCKS=7"],
+    "f_mb4": ["-DTT_FACE_MIN_BLOCKS=4"],
+    "f_mb6": ["-DTT_FACE_MIN_BLOCKS=6"],
+    "f_b256": ["-DTT_FACE_BLOCK=256", "-DTT_FACE_MIN_BLOCKS=2"],
+    "f_b192": ["-DTT_FACE_BLOCK=192", "-DTT_FACE_MIN_BLOCKS=3"],
+    "f_nofast": ["-DTT_FACE_FASTPATH=0"],
+}
 R1 = os.environ.get("TT_R1_COMMIT", "73762f2")
 
 
@@ -43,6 +54,18 @@ def main():
                         "-lcufft", "-Xlinker", "-rpath," + cuda_lib], check=True)
         print(lib)
 
+    for tag, flags in FACE_VARIANTS.items():
+        if tag not in only:                      # only on request
+            continue
+        fobjs = [os.path.join(B.OBJ, s[:-3] + ".o") for s in B.SOURCES if s != "trace_face.cu"]
+        obj = os.path.join(out, f"trace_face_{tag}.o")
+        subprocess.run([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B.CSRC, "trace_face.cu"), "-o", obj], check=True)
+        lib = os.path.join(out, f"libtt_b200_{tag}.so")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, obj, *fobjs, "-L" + cuda_lib,
+                        "-lcufft", "-Xlinker", "-rpath," + cuda_lib], check=True)
+        print(lib)
+    if only and all(t.startswith("f_") for t in only):
+        return
     for tag, flags in VARIANTS.items():
         if only and tag not in only:
             continue

@@ -24,6 +24,12 @@ def test_shard_range_partitions_exactly():
         ttd.shard_range(10, 2, 2)
 
 
+def test_upload_cube_sharded_single_process():
+    a = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+    t = ttd.upload_cube_sharded(a, device=torch.device("cpu"))
+    assert t.dtype == torch.float64 and np.array_equal(t.numpy(), a)
+
+
 def test_single_process_collectives_are_identity():
     h = [torch.arange(6).reshape(2, 3), torch.ones(4, dtype=torch.int64)]
     out = ttd.allreduce_histograms(h)
@@ -53,6 +59,13 @@ def _worker(rank, world, port, tmp):
         ne = torch.arange(125, dtype=torch.float32).reshape(5, 5, 5)
     ttd.broadcast_cube(ne, src=0)
     assert torch.equal(ne, torch.arange(125, dtype=torch.float32).reshape(5, 5, 5))
+    # host cube -> every rank's device: each rank uploads its slice, one all-gather (odd size: the last slice is short)
+    rng0 = np.random.RandomState(11)
+    host = rng0.rand(7, 5, 3).astype(np.float32)
+    mine = host.copy()
+    lo = (rank * 53) % host.size                    # whatever lies outside this rank's slice is never read
+    got = ttd.upload_cube_sharded(mine, device=torch.device("cpu"))
+    assert got.shape == host.shape and got.dtype == torch.float32 and np.array_equal(got.numpy(), host)
     # one global bundle of detector-plane rays, sharded; per-rank histograms from the oracle
     rng = np.random.RandomState(3)
     n = 5001

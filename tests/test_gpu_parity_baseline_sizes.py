@@ -358,3 +358,64 @@ def test_face_coefficient_kernel_against_corner_grid_kernel_and_abi(tt):
     c64.init_beam(10, BEAM, DIV, seed=1)
     with pytest.raises(ValueError):
         c64.solve()
+
+
+@pytest.mark.parametrize("bin_scale", [10, 5, 1])
+def test_privatised_histogram_equals_numpy_and_the_general_kernel(tt, bin_scale):
+    """optics_hist_smem16_kernel (the whole image as 16-bit counters in one CTA's shared memory; taken for >= 65536 rays in
+    storage order when the image fits: bin_scale 10; at 5 and 1 it does not fit -> general kernel) against
+    numpy.histogram2d on the same detector-plane rays and against the general kernel (forced by an identity permutation):
+    3e6 unsorted rays with NaNs, rays on bin edges and outside the detector."""
+    import torch
+    rtm = tt.ray_transfer_matrix
+    rng = np.random.default_rng(12)
+    n = 3_000_000
+    r0 = np.empty((4, n))
+    r0[0] = rng.uniform(-11e-3, 11e-3, n)          # m; the detector is 18 x 13.5 mm: some rays miss it
+    r0[2] = rng.uniform(-8e-3, 8e-3, n)
+    r0[1] = rng.normal(0, 2e-3, n)
+    r0[3] = rng.normal(0, 2e-3, n)
+    r0[0, :1000] = np.nan                          # dropped like numpy does after the reference's NaN filter
+    r0[0, 1000:1010] = 9e-3                        # last edge: inclusive
+    r0[0, 1010:1020] = -9e-3
+    sh = rtm.Shadowgraphy(r0)
+    sh.solve()
+    sh.histogram(bin_scale=bin_scale)
+    H = sh.H.copy()
+    rf = np.asarray(sh.rf)
+    ok = ~np.isnan(rf[0]) & ~np.isnan(rf[2])
+    Href = np.histogram2d(rf[0][ok], rf[2][ok], bins=[3448 // bin_scale, 2574 // bin_scale],
+                          range=[[-9.0, 9.0], [-6.75, 6.75]])[0].T
+    np.testing.assert_array_equal(H, Href)
+    sh2 = rtm.Shadowgraphy(r0)
+    sh2.use_ray_order(torch.arange(n, dtype=torch.int32, device="cuda"))      # identity order: the general kernel
+    sh2.solve()
+    sh2.histogram(bin_scale=bin_scale)
+    np.testing.assert_array_equal(sh2.H, H)
+    assert H.sum() > 0.6 * n
+
+
+def test_privatised_histogram_counter_overflow(tt):
+    """A focused beam: 12e6 of 16e6 rays fall into TWO neighbouring bins that share one 32-bit word of the privatised image
+    (and 2e6 into the last bin of the image), > 32767 per CTA and bin, so every CTA moves 0x8000-blocks of counts to the
+    global image many times while its neighbours keep adding to the same word; the image must still equal
+    numpy.histogram2d's, count for count."""
+    rtm = tt.ray_transfer_matrix
+    rng = np.random.default_rng(5)
+    n = 16_000_000
+    r0 = np.zeros((4, n))
+    r0[0] = rng.uniform(-8.9e-3, 8.9e-3, n)
+    r0[2] = rng.uniform(-6.7e-3, 6.7e-3, n)
+    dx = 18e-3 / 344                                # one bin in x at bin_scale = 10 (m)
+    r0[0, :6_000_000] = 0.25 * dx;  r0[2, :6_000_000] = 1e-5       # bin (172, 128): even ...
+    r0[0, 6_000_000:12_000_000] = 1.25 * dx; r0[2, 6_000_000:12_000_000] = 1e-5      # ... and its odd neighbour
+    r0[0, 12_000_000:14_000_000] = 8.99e-3; r0[2, 12_000_000:14_000_000] = 6.74e-3    # last bin of the image
+    perm = rng.permutation(n)
+    r0 = np.ascontiguousarray(r0[:, perm])
+    sh = rtm.Shadowgraphy(r0)
+    sh.solve()
+    sh.histogram(bin_scale=10)
+    rf = np.asarray(sh.rf)
+    Href = np.histogram2d(rf[0], rf[2], bins=[344, 257], range=[[-9.0, 9.0], [-6.75, 6.75]])[0].T
+    np.testing.assert_array_equal(sh.H, Href)
+    assert sh.H.sum() == n and sh.H.max() >= 6_000_000
