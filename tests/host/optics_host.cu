@@ -10,6 +10,7 @@ extern "C" int host_optics_hist(const double* rf_in, long np, double pos_scale, 
     OpticsArgs A;
     for (int i = 0; i < n_ops; ++i) A.ops[i] = program[i];
     A.n_ops = n_ops; A.pos_scale = pos_scale; A.nbx = nbx; A.nby = nby; A.np = np;
+    prepare_program(A);
     for (long ray = 0; ray < np; ++ray) {
         double x = rf_in[ray] * A.pos_scale, th = rf_in[np + ray];
         double y = rf_in[2 * np + ray] * A.pos_scale, ph = rf_in[3 * np + ray];

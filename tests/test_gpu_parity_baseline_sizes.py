@@ -360,22 +360,23 @@ def test_face_coefficient_kernel_against_corner_grid_kernel_and_abi(tt):
         c64.solve()
 
 
-@pytest.mark.parametrize("bin_scale", [10, 5, 1])
-def test_privatised_histogram_equals_numpy_and_the_general_kernel(tt, bin_scale):
+@pytest.mark.parametrize("bin_scale,n", [(10, 3_000_000), (10, 2_999_999), (10, 70_001), (5, 3_000_000), (1, 3_000_000)])
+def test_privatised_histogram_equals_numpy_and_the_general_kernel(tt, bin_scale, n):
     """optics_hist_smem16_kernel (the whole image as 16-bit counters in one CTA's shared memory; taken for >= 65536 rays in
     storage order when the image fits: bin_scale 10; at 5 and 1 it does not fit -> general kernel) against
     numpy.histogram2d on the same detector-plane rays and against the general kernel (forced by an identity permutation):
-    3e6 unsorted rays with NaNs, rays on bin edges and outside the detector."""
+    3e6 unsorted rays with NaNs (in x only, in theta only), rays on bin edges and outside the detector; an odd ray count
+    takes the kernel's scalar-load instantiation, 70 001 rays leave most CTAs a partial or empty batch."""
     import torch
     rtm = tt.ray_transfer_matrix
     rng = np.random.default_rng(12)
-    n = 3_000_000
     r0 = np.empty((4, n))
     r0[0] = rng.uniform(-11e-3, 11e-3, n)          # m; the detector is 18 x 13.5 mm: some rays miss it
     r0[2] = rng.uniform(-8e-3, 8e-3, n)
     r0[1] = rng.normal(0, 2e-3, n)
     r0[3] = rng.normal(0, 2e-3, n)
     r0[0, :1000] = np.nan                          # dropped like numpy does after the reference's NaN filter
+    r0[1, 2000:2500] = np.nan                      # a NaN angle makes the whole column NaN at the first element
     r0[0, 1000:1010] = 9e-3                        # last edge: inclusive
     r0[0, 1010:1020] = -9e-3
     sh = rtm.Shadowgraphy(r0)

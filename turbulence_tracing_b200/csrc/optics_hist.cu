@@ -15,8 +15,8 @@
 // 177 KB at the default binning) every ray is binned with a shared-memory atomic whatever order the rays arrive in, each
 // ray is read once, and 1e8 scattered global atomics become 148 coalesced flushes of the image.  Two counters share a
 // 32-bit word; a counter never carries into its neighbour: the add that takes a counter from 0x7FFF to 0x8000 (seen in the
-// value atomicAdd returns) makes its thread move 0x8000 counts to the global image, and a CTA-wide barrier per batch of
-// kSmemThreads x kSmemUnroll = 2048 rays bounds what the other threads can add in between (0x7FFF + 2048 < 0xFFFF; the
+// value atomicAdd returns) makes its thread move 0x8000 counts to the global image, and a CTA-wide barrier per two batches of
+// kSmemThreads x kSmemUnroll = 2048 rays bounds what the other threads can add in between (0x7FFF + 4096 < 0xFFFF; the
 // subtraction lands before the barrier, so every counter is <= 0x7FFF at every barrier).  The next batch's loads are issued
 // before the current batch is binned: the barrier does not drain the memory pipeline.
 // (Measured and rejected: the image split over the shared memories of a 2-CTA cluster, 32-bit counters, both CTAs reading
@@ -28,19 +28,11 @@
 namespace tt {
 
 static constexpr int kSmemThreads = 512;
-static constexpr int kSmemUnroll = 4;
+static constexpr int kSmemUnroll = 4;                        // rays per thread and batch
+static constexpr int kSmemChunk = kSmemThreads * kSmemUnroll;      // a batch = 2048 consecutive rays
 
-// bin_of() on edges held in shared memory, the scale hoisted out of the ray loop: the two walks settle on the bin numpy's
-// searchsorted finds wherever the first guess lands, so the result is bin_of()'s
-__device__ __forceinline__ int bin_of_staged(double x, const double* e, int nb, double lo, double hi, double scale) {
-    if (!(x >= lo && x <= hi)) return -1;
-    int b = (int)((x - lo) * scale);
-    b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
-    while (b > 0 && x < e[b]) --b;
-    while (b < nb - 1 && x >= e[b + 1]) ++b;
-    return b;
-}
-
+// VEC: the four rows of rf_in are 16-byte aligned (even ray count): a thread loads its rays as two double2 per row
+template <bool VEC>
 __global__ void __launch_bounds__(kSmemThreads, 1)
 optics_hist_smem16_kernel(const double* __restrict__ rf_in, const double* __restrict__ xe, const double* __restrict__ ye,
                           unsigned long long* __restrict__ H, OpticsArgs A, int nwords, long niter) {
@@ -54,44 +46,64 @@ optics_hist_smem16_kernel(const double* __restrict__ rf_in, const double* __rest
     __syncthreads();
     const double xlo = sx[0], xhi = sx[A.nbx], xs = (double)A.nbx / (xhi - xlo);
     const double ylo = sy[0], yhi = sy[A.nby], ys = (double)A.nby / (yhi - ylo);
-    const long nthreads = (long)gridDim.x * kSmemThreads;
-    const long t0 = (long)blockIdx.x * kSmemThreads + threadIdx.x;
-    double cur[kSmemUnroll][4], nxt[kSmemUnroll][4];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    // batch `it` of this CTA = rays [c * 2048, (c + 1) * 2048), c = it * gridDim.x + blockIdx.x; the thread's rays in it:
+    // 2 t, 2 t + 1, 1024 + 2 t, 1024 + 2 t + 1 (constant offsets from one address per row)
+    double bufa[4][kSmemUnroll], bufb[4][kSmemUnroll];       // [row][ray]
 #define TT_HIST_LOAD(buf, it)                                                                                    \
-    _Pragma("unroll") for (int k = 0; k < kSmemUnroll; ++k) {                                                    \
-        const long i = t0 + ((it) * kSmemUnroll + k) * nthreads;                                                 \
-        if (i < A.np) {                                                                                          \
-            buf[k][0] = __ldg(rf_in + i); buf[k][1] = __ldg(rf_in + A.np + i);                                   \
-            buf[k][2] = __ldg(rf_in + 2 * A.np + i); buf[k][3] = __ldg(rf_in + 3 * A.np + i);                    \
+    {                                                                                                            \
+        const long first = ((it) * (long)gridDim.x + blockIdx.x) * kSmemChunk;                                   \
+        const double* p = rf_in + first + 2 * threadIdx.x;                                                       \
+        if (VEC && first + kSmemChunk <= A.np) {                                                                 \
+            _Pragma("unroll") for (int m = 0; m < 4; ++m) {                                                      \
+                const double2 v0 = __ldg(reinterpret_cast<const double2*>(p + m * A.np));                        \
+                const double2 v1 = __ldg(reinterpret_cast<const double2*>(p + m * A.np + kSmemChunk / 2));       \
+                buf[m][0] = v0.x; buf[m][1] = v0.y; buf[m][2] = v1.x; buf[m][3] = v1.y;                          \
+            }                                                                                                    \
+        } else {                                             /* the last batch, batches behind it, odd alignment */ \
+            _Pragma("unroll") for (int k = 0; k < kSmemUnroll; ++k) {                                            \
+                const long i = first + 2 * threadIdx.x + (k & 1) + (k >> 1) * (kSmemChunk / 2);                  \
+                _Pragma("unroll") for (int m = 0; m < 4; ++m) buf[m][k] = i < A.np ? __ldg(rf_in + m * A.np + i) : nan;   \
+            }                                                                                                    \
         }                                                                                                        \
     }
-    TT_HIST_LOAD(cur, 0L)
-    for (long it = 0; it < niter; ++it) {                    // the same trip count for every thread: barrier inside
-        if (it + 1 < niter) { TT_HIST_LOAD(nxt, it + 1) }
-#pragma unroll
-        for (int k = 0; k < kSmemUnroll; ++k) {
-            const long i = t0 + (it * kSmemUnroll + k) * nthreads;
-            if (i >= A.np) continue;
-            double X = cur[k][0] * A.pos_scale, T = cur[k][1], Y = cur[k][2] * A.pos_scale, P = cur[k][3];
-            apply_program(A, X, T, Y, P);
-            const int ix = bin_of_staged(X, sx, A.nbx, xlo, xhi, xs), iy = bin_of_staged(Y, sy, A.nby, ylo, yhi, ys);
-            if (ix >= 0 && iy >= 0) {
-                const int b = iy * A.nbx + ix;
-                const unsigned sh = (unsigned)(b & 1) * 16u;
-                const unsigned old = atomicAdd(words + (b >> 1), 1u << sh);
-                if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {    // this add made it 0x8000: move them out
-                    atomicSub(words + (b >> 1), 0x8000u << sh);
-                    atomicAdd(&H[b], 0x8000ull);
-                }
-            }
-        }
+    // one batch: kSmemUnroll rays per thread side by side through the program (independent chains), then binned; a ray
+    // behind the end is a NaN column and falls out at the bin search
+#define TT_HIST_BIN(buf)                                                                                         \
+    {                                                                                                            \
+        _Pragma("unroll") for (int k = 0; k < kSmemUnroll; ++k) { buf[0][k] *= A.pos_scale; buf[2][k] *= A.pos_scale; }   \
+        bool dead[kSmemUnroll];                                                                                  \
+        run_program_n<kSmemUnroll>(A, buf[0], buf[1], buf[2], buf[3], dead);                                     \
+        int b[kSmemUnroll];                                                                                      \
+        _Pragma("unroll") for (int k = 0; k < kSmemUnroll; ++k) {                                                \
+            /* a NaN in any row drops the ray (x, y: the bin search; theta, phi: here), unless the program is empty */ \
+            if (A.n_ops > 0) dead[k] = dead[k] || buf[1][k] != buf[1][k] || buf[3][k] != buf[3][k];              \
+            const int ix = bin_of_scaled<false>(buf[0][k], sx, A.nbx, xlo, xhi, xs);                             \
+            const int iy = bin_of_scaled<false>(buf[2][k], sy, A.nby, ylo, yhi, ys);                             \
+            b[k] = (!dead[k] && ix >= 0 && iy >= 0) ? iy * A.nbx + ix : -1;                                      \
+        }                                                                                                        \
+        _Pragma("unroll") for (int k = 0; k < kSmemUnroll; ++k) {                                                \
+            if (b[k] < 0) continue;                                                                              \
+            const unsigned sh = (unsigned)(b[k] & 1) * 16u;                                                      \
+            const unsigned old = atomicAdd(words + (b[k] >> 1), 1u << sh);                                       \
+            if (((old >> sh) & 0xFFFFu) == 0x7FFFu) { /* this add made it 0x8000: move them out */               \
+                atomicSub(words + (b[k] >> 1), 0x8000u << sh);                                                   \
+                atomicAdd(&H[b[k]], 0x8000ull);                                                                  \
+            }                                                                                                    \
+        }                                                                                                        \
+    }
+    // two batches per turn, the buffers taking turns (no register copies); every thread makes the same number of turns
+    // (the barrier), batches behind the end of the rays are empty.  Adds between two barriers: 2 x 2048 < 0x8000.
+    TT_HIST_LOAD(bufa, 0L)
+    for (long it = 0; it < niter; it += 2) {
+        TT_HIST_LOAD(bufb, it + 1)
+        TT_HIST_BIN(bufa)
+        TT_HIST_LOAD(bufa, it + 2)
+        TT_HIST_BIN(bufb)
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kSmemUnroll; ++k)
-#pragma unroll
-            for (int m = 0; m < 4; ++m) cur[k][m] = nxt[k][m];
     }
 #undef TT_HIST_LOAD
+#undef TT_HIST_BIN
     const int nbins = A.nbx * A.nby;
     for (int i = threadIdx.x; i < nwords; i += kSmemThreads) {
         const unsigned w = words[i];
@@ -113,18 +125,20 @@ static int launch_smem16_hist(const double* rf_in, const double* xe, const doubl
     static std::atomic<int> attr_set[64];                    // per device: the attribute belongs to the device's copy of the kernel
     if (dev < 0 || dev >= 64) return TT_ERR_UNSUPPORTED;
     if (!attr_set[dev].load()) {
-        if (cudaFuncSetAttribute(optics_hist_smem16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess) {
+        if (cudaFuncSetAttribute(optics_hist_smem16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess ||
+            cudaFuncSetAttribute(optics_hist_smem16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess) {
             (void)cudaGetLastError();
             return TT_ERR_UNSUPPORTED;
         }
         attr_set[dev].store(1);
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long per = (long)kSmemThreads * kSmemUnroll;
-    long blocks = (A.np + per - 1) / per;
-    if (blocks > sms) blocks = sms;                          // one CTA per SM (shared-memory limited)
-    const long niter = (A.np + blocks * per - 1) / (blocks * per);
-    optics_hist_smem16_kernel<<<(unsigned)blocks, kSmemThreads, smem, s>>>(rf_in, xe, ye, H, A, (int)nwords, niter);
+    const long chunks = (A.np + kSmemChunk - 1) / kSmemChunk;
+    const long blocks = chunks < sms ? chunks : sms;         // one CTA per SM (shared-memory limited)
+    const long niter = (chunks + blocks - 1) / blocks;
+    const bool vec = (reinterpret_cast<uintptr_t>(rf_in) % 16 == 0) && (A.np % 2 == 0);
+    if (vec) optics_hist_smem16_kernel<true><<<(unsigned)blocks, kSmemThreads, smem, s>>>(rf_in, xe, ye, H, A, (int)nwords, niter);
+    else optics_hist_smem16_kernel<false><<<(unsigned)blocks, kSmemThreads, smem, s>>>(rf_in, xe, ye, H, A, (int)nwords, niter);
     if (cudaPeekAtLastError() != cudaSuccess) {              // could not be launched: the general kernel does it
         (void)cudaGetLastError();
         return TT_ERR_UNSUPPORTED;
@@ -135,6 +149,7 @@ static int launch_smem16_hist(const double* rf_in, const double* xe, const doubl
 
 static constexpr int kThreads = 256;
 static constexpr int kRaysPerThread = 8;
+static constexpr int kGroup = 4;          // rays a thread takes through the program side by side
 static constexpr int kTile = 64;
 
 __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __restrict__ rf_in,
@@ -152,27 +167,45 @@ __global__ void __launch_bounds__(kThreads) optics_hist_kernel(const double* __r
     __syncthreads();
 
     const long base = (long)blockIdx.x * (kThreads * kRaysPerThread);
+    double xlo = 0, xhi = 0, xs = 0, ylo = 0, yhi = 0, ys = 0;
+    if (H || Hw) {
+        xlo = ldg_f64(xe); xhi = ldg_f64(xe + A.nbx); xs = (double)A.nbx / (xhi - xlo);
+        ylo = ldg_f64(ye); yhi = ldg_f64(ye + A.nby); ys = (double)A.nby / (yhi - ylo);
+    }
     int bx[kRaysPerThread], by[kRaysPerThread];
     int mnx = 0x7fffffff, mny = 0x7fffffff;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
-    for (int k = 0; k < kRaysPerThread; ++k) {
-        const long i = base + (long)k * kThreads + threadIdx.x;
-        bx[k] = by[k] = -1;
-        if (i < A.np) {
-            const long ray = perm ? (long)perm[i] : i;
-            double x = rf_in[ray] * A.pos_scale, th = rf_in[A.np + ray];
-            double y = rf_in[2 * A.np + ray] * A.pos_scale, ph = rf_in[3 * A.np + ray];
-            apply_program(A, x, th, y, ph);
+    for (int g = 0; g < kRaysPerThread; g += kGroup) {       // kGroup rays side by side: loads first, then the program
+        long ray[kGroup];
+        double x[kGroup], th[kGroup], y[kGroup], ph[kGroup];
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) {
+            const long i = base + (long)(g + k) * kThreads + threadIdx.x;
+            ray[k] = -1;
+            x[k] = th[k] = y[k] = ph[k] = nan;
+            if (i < A.np) {
+                ray[k] = perm ? (long)perm[i] : i;
+                x[k] = rf_in[ray[k]]; th[k] = rf_in[A.np + ray[k]]; y[k] = rf_in[2 * A.np + ray[k]]; ph[k] = rf_in[3 * A.np + ray[k]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) { x[k] *= A.pos_scale; y[k] *= A.pos_scale; }
+        apply_program_n<kGroup>(A, x, th, y, ph);
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) {
+            bx[g + k] = by[g + k] = -1;
+            if (ray[k] < 0) continue;
             if (rf_out) {
-                rf_out[ray] = x; rf_out[A.np + ray] = th; rf_out[2 * A.np + ray] = y; rf_out[3 * A.np + ray] = ph;
+                rf_out[ray[k]] = x[k]; rf_out[A.np + ray[k]] = th[k]; rf_out[2 * A.np + ray[k]] = y[k]; rf_out[3 * A.np + ray[k]] = ph[k];
             }
             if (H || Hw) {
-                const int ix = bin_of(x, xe, A.nbx), iy = bin_of(y, ye, A.nby);
+                const int ix = bin_of_scaled<true>(x[k], xe, A.nbx, xlo, xhi, xs), iy = bin_of_scaled<true>(y[k], ye, A.nby, ylo, yhi, ys);
                 if (ix >= 0 && iy >= 0) {
-                    bx[k] = ix; by[k] = iy;
+                    bx[g + k] = ix; by[g + k] = iy;
                     mnx = min(mnx, ix); mny = min(mny, iy);
                     // weighted image (numpy.histogram2d(weights=)): FP64 atomics straight to global
-                    if (Hw) atomicAdd(&Hw[(size_t)iy * A.nbx + ix], weights[ray]);
+                    if (Hw) atomicAdd(&Hw[(size_t)iy * A.nbx + ix], weights[ray[k]]);
                 }
             }
         }
@@ -226,6 +259,7 @@ extern "C" int tt_optics_hist_weighted(const double* rf_in_dev, long np, const u
     }
     A.n_ops = n_ops; A.pos_scale = pos_scale; A.nbx = nbx; A.nby = nby; A.np = np;
     if (np == 0) return TT_OK;
+    prepare_program(A);                                      // -1/f, r^2: once, not per ray
     // the image alone, rays in storage order, and it fits a CTA's shared memory as 16-bit counters: privatised binning
     if (H_dev && !Hw_dev && !rf_out_dev && !perm_dev && np >= (1L << 16) &&
         launch_smem16_hist(rf_in_dev, xedges_dev, yedges_dev, H_dev, A, (cudaStream_t)stream) == TT_OK)

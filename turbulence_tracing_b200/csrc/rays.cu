@@ -92,8 +92,12 @@ extern "C" int tt_sort_rays(const double* s0_dev, long np, int par, const double
                                                        65536.0 / wu, 65536.0 / wv, keys_in, idx_in);
     rc = launch_check("morton_key_kernel");
     if (rc) return rc;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, perm_dev, (int)np, 0,
-                                                    32, s);
+    // only the leading bits that resolve a quarter of a cell: a 513^3 cube sorts 22 bits (3 radix passes instead of 4);
+    // rays within one such box keep their storage order (the sort is stable), a ray's result does not depend on its place
+    int cells = (n_xyz[au] > n_xyz[av] ? n_xyz[au] : n_xyz[av]) - 1, bits = 2;
+    while ((1 << (bits - 2)) < cells && bits < 16) ++bits;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, perm_dev, (int)np,
+                                                    32 - 2 * bits, 32, s);
     if (e != cudaSuccess) return cuda_fail(e, "cub::DeviceRadixSort::SortPairs");
     return TT_OK;
 }
