@@ -34,7 +34,8 @@ FACE_VARIANTS = {
     "f_mb6": ["-DTT_FACE_MIN_BLOCKS=6"],
     "f_b256": ["-DTT_FACE_BLOCK=256", "-DTT_FACE_MIN_BLOCKS=2"],
     "f_b192": ["-DTT_FACE_BLOCK=192", "-DTT_FACE_MIN_BLOCKS=3"],
-    "f_nofast": ["-DTT_FACE_FASTPATH=0"],
+    "f_nofast": ["-DTT_FACE_REBASE=0", "-DTT_FACE_FASTPATH=0"],
+    "f_norebase": ["-DTT_FACE_REBASE=0"],                           # the round-2 v4 loop (warp-vote fast path + general step)
 }
 R1 = os.environ.get("TT_R1_COMMIT", "73762f2")
 

@@ -103,6 +103,11 @@ TT_HD FaceQ face_add(const FaceQ& f, const FaceQ& b) {
     r.zac = add2(f.zac, b.zac); r.zbd = add2(f.zbd, b.zbd);
     return r;
 }
+TT_HD FaceQ face_scale(const FaceQ& f, f32x2 C) {
+    FaceQ r;
+    r.a = mul2(f.a, C); r.b = mul2(f.b, C); r.c = mul2(f.c, C); r.d = mul2(f.d, C); r.zac = mul2(f.zac, C); r.zbd = mul2(f.zbd, C);
+    return r;
+}
 TT_HD FaceQ face_at(const FaceQ& base, const FaceQ& primed, f32x2 FW) {
     FaceQ r;
     r.a = fma2(FW, primed.a, base.a); r.b = fma2(FW, primed.b, base.b); r.c = fma2(FW, primed.c, base.c);
@@ -117,6 +122,18 @@ TT_HD void face_eval(const FaceQ& q, f32x2 tuv, f32x2& guv, float& gw) {
     gw = fmaf(hi2(tuv), hi2(r), lo2(r));
 }
 
+#ifndef TT_FACE_REBASE
+#define TT_FACE_REBASE 0       // (measured, not adopted: 305.3 vs 302.9 ms on 513^3 / 1e8 rays -- see below) every step runs the whole-cell arithmetic on the polynomial of ITS OWN w-interval: a lane
+                               // that starts inside a cell (after a side crossing, or launched inside the cube) or stops at
+                               // a side face rebases (B, P) once -- B' = B + fw P, P' = h P -- instead of the whole warp
+                               // evaluating B + (fw + c h) P at every stage of every step in which any lane does.  No
+                               // warp vote, one instantiation of the step: a ray's arithmetic never depends on its warp.
+                               // ncu (r02_trace_face_v7_c3): the loop body is 112 instructions for every step instead of
+                               // ~100 / ~150 (2/3 fast, 1/3 general), but a quarter of the warp's steps hold a side crossing
+                               // of some lane and the prediction + column change with the rebase arithmetic cost ~112
+                               // instructions there (1.6 lanes active): 139.6 vs 134.8 warp-instructions per warp-step.
+                               // Host-tested (tests/test_host_kernels.py builds either form), GPU suite green with it.
+#endif
 #ifndef TT_FACE_FASTPATH
 #define TT_FACE_FASTPATH 1     // warp-uniform shortcut for whole-cell steps: when every lane of the warp starts ON its
                                // plane and no lane predicts a side crossing, the stage coefficients are the base face,
@@ -216,6 +233,60 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
         FaceQ B = face_ld(p), P;
         FaceW N;
         P = face_sub(face_ld(p + fplane), B);
+#if TT_FACE_REBASE
+        // (B, P) = the polynomial at the start of the step and its change over the step's w-interval [fw, fw + h]
+        if (fw != 0.f) { B = face_at(B, P, bc2(fw)); P = face_scale(P, bc2(1.f - fw)); }       // launched inside a cell
+        while (true) {
+            // face k+2, consumed when the ray arrives at plane k+1.  Unconditional (a predicated load goes through
+            // temporaries and 12 moves): the grid carries one spare plane behind the last face
+            N = face_ldw(p + 2 * fplane);
+            const float q = trcp<float>(dw);        // (dw > TT_MARCH_MIN_DW: checked at the entry and after every step)
+            const f32x2 aUV = mul2(duv, bc2(q));
+            float h = 1.f - fw;
+            int cross = 0;
+            {
+                const f32x2 puv = fma2(bc2(h), aUV, tuv);
+                const float pu = lo2(puv), pv = hi2(puv);
+                if (fabsf(pu) > 0.5f || fabsf(pv) > 0.5f) {
+                    const float aU = lo2(aUV), aV = hi2(aUV), tu = lo2(tuv), tv = hi2(tuv);
+                    float lu = 2.f, lv = 2.f;
+                    if (aU > 0.f) lu = chord_fraction<float>(0.5f - tu, h * aU); else if (aU < 0.f) lu = chord_fraction<float>(-0.5f - tu, h * aU);
+                    if (aV > 0.f) lv = chord_fraction<float>(0.5f - tv, h * aV); else if (aV < 0.f) lv = chord_fraction<float>(-0.5f - tv, h * aV);
+                    float lam = fminf(lu, lv);
+                    if (lam < 1.f) {
+                        cross = lu <= lv ? (aU > 0.f ? 1 : -1) : (aV > 0.f ? 2 : -2);
+                        lam = lam > 0.f ? lam : 0.f;
+                        h *= lam;
+                        P = face_scale(P, bc2(lam));                          // the step stops at the side face
+                    }
+                }
+            }
+            f32x2 g; float gw;
+            face_eval(B, tuv, g, gw);
+            const bool ok = face_step<true, TRACK_S>(B, P, tuv, duv, dw, s, 0.f, h, q, aUV, mul2(g, bc2(q)), gw * q);
+            if (!(ok && dw > (float)TT_MARCH_MIN_DW)) { fast = false; break; }
+            if (cross == 0) {
+                ++steps;
+                fw = 0.f;
+                if (++k >= nw - 1) break;
+                p += fplane;
+                P = face_sub(face_pack(N), B);                                // B is the far face by now: the next base
+            } else {
+                fw += h;
+                float tu = lo2(tuv), tv = hi2(tuv);
+                int dp = 0;
+                if (cross == 1) { ++cu; tu -= 1.f; dp = 3; } else if (cross == -1) { --cu; tu += 1.f; dp = -3; }
+                else if (cross == 2) { ++cv; tv -= 1.f; dp = row3; } else { --cv; tv += 1.f; dp = -row3; }
+                p += dp;
+                tuv = pk2(tu, tv);
+                if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }      // side exit
+                const FaceQ Bn = face_ld(p);                                  // both faces of the new cell column
+                const FaceQ Pn = face_sub(face_ld(p + fplane), Bn);
+                B = face_at(Bn, Pn, bc2(fw));                                 // rebased to the rest of the cell
+                P = face_scale(Pn, bc2(1.f - fw));
+            }
+        }
+#else
         while (true) {
             // face k+2, consumed at the end of the step.  Unconditional (a predicated load goes through temporaries and
             // 12 moves): the grid carries one spare plane behind the last face for the load issued in the last cell
@@ -281,6 +352,7 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
             }
             P = face_sub(face_pack(N), B);
         }
+#endif
     }
     if (!fast) {
         status[ray] = TT_RAY_DEFERRED;
