@@ -162,6 +162,18 @@ int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* g
                  double* rf_dev, double* sf_dev, double* aux_out_dev,
                  unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
 
+/* The aux4_dev grid of tt_trace_aux from the user's cubes in one pass: (B_u, B_v, B_w, kappa) per node in the gradient
+ * grid's layout and dtype (grid_dtype).  Reference: only the call sites exist upstream (example_kitchensink.py:72-101:
+ * external_B / external_Te / external_Z, B_on / inv_brems); the formula is the NRL-formulary inverse-bremsstrahlung
+ * coefficient documented at ElectronCube.kappa(): kappa[1/m] = 100 * 3.1e-7 Z ne^2 lnL Te^-3/2 / (omega^2 sqrt(1 - ne/nc)),
+ * ne in cm^-3, Te in eV, ne/nc clipped at ne_max, lnL = coulomb_log or, if that is NaN, max(2, 24 - ln(sqrt(ne)/Te)).
+ * ne_dev[ix][iy][iz] (ne_dtype); Te_dev / Z_dev: cubes of aux_dtype or NULL (then Te_scalar / Z_scalar);
+ * B_dev[ix][iy][iz][3] (aux_dtype, xyz components) or NULL (B = 0); want_kappa = 0 leaves kappa = 0.               */
+int tt_build_aux_grid(const void* ne_dev, int ne_dtype, const void* Te_dev, double Te_scalar, const void* Z_dev,
+                      double Z_scalar, const void* B_dev, int aux_dtype, const int n_xyz[3], int par, double nc,
+                      double ne_max, double omega, double coulomb_log, int want_kappa, void* aux4_dev, int grid_dtype,
+                      tt_stream_t stream);
+
 /* ---- rectilinear grids: axes whose nodes are NOT equally spaced ------------------------------------
  * The reference takes any ascending coordinate arrays: numpy.gradient(ne_nc, x, axis=0) uses the
  * non-uniform second-order stencil and RegularGridInterpolator((x, y, z), ...) locates cells by

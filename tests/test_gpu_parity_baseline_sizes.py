@@ -420,3 +420,47 @@ def test_privatised_histogram_counter_overflow(tt):
     Href = np.histogram2d(rf[0], rf[2], bins=[344, 257], range=[[-9.0, 9.0], [-6.75, 6.75]])[0].T
     np.testing.assert_array_equal(sh.H, Href)
     assert sh.H.sum() == n and sh.H.max() >= 6_000_000
+
+
+@pytest.mark.parametrize("direction", ["x", "y", "z"])
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+def test_fused_aux_grid_equals_the_elementwise_composition(tt, direction, dt):
+    """tt_build_aux_grid ((B_u, B_v, B_w, kappa) per node in the gradient grid's layout, one pass) against the composition
+    it replaced: kappa() (the documented formula, element-wise tensor operations) and the frame permutation of B, on a
+    non-cubic cube with Te and Z as cubes, as scalars, with a fixed Coulomb logarithm, with B only and with kappa only."""
+    import torch
+    pt = tt.particle_tracker
+    rng = np.random.default_rng(8)
+    x, y, z = np.linspace(-5e-3, 5e-3, 23), np.linspace(-4e-3, 4e-3, 31), np.linspace(-5e-3, 5e-3, 18)
+    shape = (23, 31, 18)
+    ne = (1e25 * rng.uniform(0.0, 1.2, shape)).astype(dt)                 # some nodes above 0 density only; clip is at ne/nc
+    B = rng.standard_normal(shape + (3,)).astype(dt) * 5
+    Te = rng.uniform(20, 300, shape).astype(dt)
+    Z = rng.uniform(1, 6, shape).astype(dt)
+    fa = {"z": (0, 1, 2), "y": (0, 2, 1), "x": (1, 2, 0)}[direction]
+    for case in ("cubes", "scalars", "lnL", "B only", "kappa only"):
+        cube = pt.ElectronCube(x, y, z, direction, B_on=case != "kappa only", inv_brems=case != "B only", phaseshift=True,
+                               dtype=dt, verbose=False)
+        cube.external_ne(ne)
+        if case != "kappa only":
+            cube.external_B(B)
+        if case != "B only":
+            cube.external_Te(Te if case != "scalars" else 120.0)
+            cube.external_Z(Z if case != "scalars" else 3.0)
+        if case == "lnL":
+            cube.coulomb_log = 7.5
+        cube.calc_dndr()
+        a = cube._aux_grid()
+        assert tuple(a.shape) == (shape[fa[2]], shape[fa[1]], shape[fa[0]], 4) and str(a.dtype) == "torch." + dt
+        got = a.double().cpu().numpy()
+        if case == "kappa only":
+            assert not got[..., :3].any()
+        else:
+            want_B = np.stack([B[..., fa[0]], B[..., fa[1]], B[..., fa[2]]], axis=-1).astype(np.float64)
+            np.testing.assert_array_equal(got[..., :3], want_B.transpose(fa[2], fa[1], fa[0], 3))
+        if case == "B only":
+            assert not got[..., 3].any()
+        else:
+            kap = cube.kappa().double().cpu().numpy().transpose(fa[2], fa[1], fa[0])
+            assert np.isfinite(kap).all() and kap.max() > 0
+            np.testing.assert_allclose(got[..., 3], kap, rtol=2e-7 if dt == "float32" else 1e-14, atol=0)

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "tt_trace_faces": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
                           _vp, _vp]),
+    "tt_build_aux_grid": (_i, [_vp, _i, _vp, _d, _vp, _d, _vp, _i, C.POINTER(_I3), _i, _d, _d, _d, _d, _i, _vp, _i, _vp]),
     "tt_calc_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp]),
     "tt_trace_axes": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _vp, _l, _vp, _vp]),

@@ -231,27 +231,62 @@ class ElectronCube:
         return 100.0 * 3.1e-7 * Z * ne_cc**2 * lnL * Te**-1.5 / (self.omega**2 * disp)
 
     def _aux_grid(self):
-        """(B_u, B_v, B_w, kappa) in the layout/dtype of the gradient grid, or None (phase only)."""
+        """(B_u, B_v, B_w, kappa) in the layout/dtype of the gradient grid, or None (phase only): one pass of
+        ``tt_build_aux_grid`` over the user's cubes (no whole-cube temporaries; ``kappa()`` is the same formula as a
+        diagnostic)."""
         torch = _lib.torch_cuda()
         if not (self.B_on or self.inv_brems):
             return None
         if self._aux is not None:
             return self._aux
         grid = self._require_grid()
-        fa = self._frame
-        comps = []
+        lib = _lib.load()
+
+        def dev(v):                         # a user cube on the device in its own floating type (FP32 stays FP32)
+            t = v.torch if isinstance(v, DeviceArray) else v
+            if isinstance(t, torch.Tensor):
+                t = t.cuda()
+                return t if t.dtype in (torch.float32, torch.float64) else t.double()
+            a_ = np.asarray(t)
+            return _lib.to_device(a_, torch.float32 if a_.dtype == np.float32 else torch.float64)
+
+        ne = dev(self._ne).contiguous()
+        B = Te = Z = None
+        Te_s = Z_s = 0.0
         if self.B_on:
             if self._B is None:
                 raise AttributeError("B_on=True needs external_B(B)")
-            B = _lib.to_device(self._B, torch.float64)
+            B = dev(self._B)
             if tuple(B.shape) != self.shape + (3,):
                 raise ValueError(f"B has shape {tuple(B.shape)}, expected {self.shape + (3,)}")
-            comps = [B[..., fa[0]], B[..., fa[1]], B[..., fa[2]]]
-        else:
-            z = torch.zeros(self.shape, dtype=torch.float64, device="cuda")
-            comps = [z, z, z]
-        comps.append(self.kappa() if self.inv_brems else torch.zeros(self.shape, dtype=torch.float64, device="cuda"))
-        a = torch.stack(comps, dim=-1).permute(fa[2], fa[1], fa[0], 3).to(grid.dtype).contiguous()
+        if self.inv_brems:
+            if self._Te is None:
+                raise AttributeError("inv_brems=True needs external_Te(Te)")
+            if isinstance(self._Te, (int, float)):
+                Te_s = float(self._Te)
+            else:
+                Te = dev(self._Te)
+                if Te.numel() == 1:
+                    Te_s, Te = float(Te.item()), None
+            if isinstance(self._Z, (int, float)):
+                Z_s = float(self._Z)
+            else:
+                Z = dev(self._Z)
+                if Z.numel() == 1:
+                    Z_s, Z = float(Z.item()), None
+        cubes = [t for t in (B, Te, Z) if t is not None]
+        adt = torch.float32 if cubes and all(t.dtype == torch.float32 for t in cubes) else torch.float64
+        B, Te, Z = ((None if t is None else t.to(adt)) for t in (B, Te, Z))
+        Te, Z = ((None if t is None else t.expand(*self.shape).contiguous()) for t in (Te, Z))
+        if B is not None:
+            B = B.contiguous()
+        a = torch.empty(grid.shape, dtype=grid.dtype, device="cuda")
+        _lib.check(lib.tt_build_aux_grid(_lib.ptr(ne), _lib.dtype_code(ne.dtype), _lib.ptr(Te), Te_s, _lib.ptr(Z),
+                                         Z_s, _lib.ptr(B), _lib.dtype_code(adt), _lib.i3(self.shape), self._par, float(self.nc),
+                                         float(self.ne_max), float(self.omega),
+                                         float("nan") if self.coulomb_log is None else float(self.coulomb_log),
+                                         int(bool(self.inv_brems)), _lib.ptr(a), _lib.dtype_code(grid.dtype),
+                                         _lib.stream_ptr()), "tt_build_aux_grid")
         self._aux = a
         return a
 
