@@ -426,6 +426,7 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
     s0_dev = cube.s0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     trace_ms = []
+    hist_ms = []               # detector kernel (optics + histogram), one launch per step
     phase_events = []          # per step: events at the phase boundaries (read after the timed region)
 
     def mark(lst):
@@ -462,6 +463,7 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
             torch.distributed.barrier()
         torch.cuda.synchronize()
         c._trace_events = []                    # CUDA events around every trace launch from here on
+        rtm._kernel_events = []                 # ... and around every detector-kernel launch
         if sampler:
             sampler.start()
         l0 = int(lib.tt_launch_count())
@@ -479,6 +481,8 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
         ms = ev[0].elapsed_time(ev[1])
         trace_ms[:] = c.trace_ms()
         c._trace_events = None
+        hist_ms[:] = [a.elapsed_time(b) for a, b in rtm._kernel_events]
+        rtm._kernel_events = None
         ms = ttd.allreduce_scalar(float(ms), "max", device=dev)
         tot_steps = ttd.allreduce_scalar(int(sum(int(t.item()) for t in counters)), "sum", device=dev)
         launches = ttd.allreduce_scalar(int(launches), "sum", device=dev)
@@ -489,6 +493,7 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
     names = ["calc_dndr", "face_grid+sort+trace", "optics+hist", "allreduce"]
     phases = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in phase_events[-steps:]])) for i, n in enumerate(names)}
     phases["trace_kernel"] = kernel_ms
+    phases["detector_kernel"] = float(np.mean(hist_ms)) if hist_ms else float("nan")
     if world > 1:                        # every rank's breakdown (rank skew shows up as all-reduce wait)
         allp = [None] * world
         torch.distributed.all_gather_object(allp, phases)
@@ -627,6 +632,17 @@ def run_gpu_arm(args, wl):
         bps = 64 * (2 if dtype == "float64" else 1) * (2 if aux else 1)
         note = "4 corners of the next plane per ray-step, 16 B each in FP32 (32 B in FP64; x2 with the B/kappa grid)"
     roofline = build_roofline(key, kern, main["steps_per_launch"], main["kernel_ms"], clocks, bps, note) if not args.rays else None
+    if roofline is not None:
+        # the second kernel of the step, HBM-bound by design: 32 B per ray read once (x, theta, y, phi in FP64), image in shared memory
+        ph = main["phases_ms"][0] if isinstance(main["phases_ms"], list) else main["phases_ms"]
+        dms = ph.get("detector_kernel")
+        if dms and dms == dms:
+            peak_hbm, peak_src = measured_hbm_peak()
+            gbs = 32.0 * main["rays_per_rank"] / (dms * 1e-3) / 1e9
+            roofline["detector_kernel"] = {"bound": "hbm", "kernel": "optics_hist_smem16_kernel (optics_hist_kernel when the image does not fit shared memory)",
+                                           "kernel_ms": dms, "algorithmic_bytes_per_ray": 32, "achieved": gbs, "peak": peak_hbm,
+                                           "unit": "GB/s", "frac": gbs / peak_hbm, "peak_source": peak_src,
+                                           "note": "CUDA events around the launch inside the timed region (rank 0)"}
 
     # ---- sub-records (same machinery, fewer steps): strong scaling, configs[4] share, configs[1], configs[3], FP64, ... ----
     extra = {}
@@ -659,6 +675,13 @@ def run_gpu_arm(args, wl):
             per = WORKLOADS["c5"][1]
             f0, _ = ttd.shard_range(per * world, rank, world)
             main.pop("ne", None)
+            # 1025^3: 17 GB node grid + 52 GB face grid + 10 GB of rays.  Hand the cached blocks of the smaller workloads
+            # back first: carved out of a fragmented pool the same kernel ran 980 instead of 793 ms (measured; alone, as
+            # `--workload c5`, and at 8 GPUs behind only one other sub-record: 791-793 ms)
+            cache.clear()
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
             m = gpu_measure(ctx, args, "c5", rays_per_rank=per, first_ray=f0, dtype="float32", steps=2, warmup=1,
                             do_e2e=(not args.no_e2e and world == 8), ne_cache=cache)
             extra["c5"] = dict(compact(m), scaling="weak", workload=WORKLOADS["c5"][2] +

@@ -35,7 +35,8 @@ FACE_VARIANTS = {
     "f_b256": ["-DTT_FACE_BLOCK=256", "-DTT_FACE_MIN_BLOCKS=2"],
     "f_b192": ["-DTT_FACE_BLOCK=192", "-DTT_FACE_MIN_BLOCKS=3"],
     "f_nofast": ["-DTT_FACE_REBASE=0", "-DTT_FACE_FASTPATH=0"],
-    "f_norebase": ["-DTT_FACE_REBASE=0"],                           # the round-2 v4 loop (warp-vote fast path + general step)
+    "f_norebase": ["-DTT_FACE_REBASE=0"],
+    "f_pf2": ["-DTT_FACE_PREFETCH=2"], "f_pf4": ["-DTT_FACE_PREFETCH=4"], "f_pf8": ["-DTT_FACE_PREFETCH=8"],                           # the round-2 v4 loop (warp-vote fast path + general step)
 }
 R1 = os.environ.get("TT_R1_COMMIT", "73762f2")
 
@@ -55,17 +56,23 @@ def main():
                         "-lcufft", "-Xlinker", "-rpath," + cuda_lib], check=True)
         print(lib)
 
-    for tag, flags in FACE_VARIANTS.items():
+    other = {"h_t640": ("optics_hist.cu", ["-DTT_HIST_THREADS=640"]), "h_t768": ("optics_hist.cu", ["-DTT_HIST_THREADS=768"]),
+             "h_t384": ("optics_hist.cu", ["-DTT_HIST_THREADS=384"]), "h_new": ("optics_hist.cu", []),
+             "a_mb2": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=2"]), "a_mb4": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=4"]),
+             "a_new": ("trace_event.cu", [])}
+    by_file = {t: ("trace_face.cu", f) for t, f in FACE_VARIANTS.items()}
+    by_file.update(other)
+    for tag, (src, flags) in by_file.items():
         if tag not in only:                      # only on request
             continue
-        fobjs = [os.path.join(B.OBJ, s[:-3] + ".o") for s in B.SOURCES if s != "trace_face.cu"]
-        obj = os.path.join(out, f"trace_face_{tag}.o")
-        subprocess.run([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B.CSRC, "trace_face.cu"), "-o", obj], check=True)
+        fobjs = [os.path.join(B.OBJ, s[:-3] + ".o") for s in B.SOURCES if s != src]
+        obj = os.path.join(out, f"{src[:-3]}_{tag}.o")
+        subprocess.run([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B.CSRC, src), "-o", obj], check=True)
         lib = os.path.join(out, f"libtt_b200_{tag}.so")
         subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, obj, *fobjs, "-L" + cuda_lib,
                         "-lcufft", "-Xlinker", "-rpath," + cuda_lib], check=True)
         print(lib)
-    if only and all(t.startswith("f_") for t in only):
+    if only and all(t in by_file for t in only):
         return
     for tag, flags in VARIANTS.items():
         if only and tag not in only:

@@ -16,7 +16,7 @@
 // ray is read once, and 1e8 scattered global atomics become 148 coalesced flushes of the image.  Two counters share a
 // 32-bit word; a counter never carries into its neighbour: the add that takes a counter from 0x7FFF to 0x8000 (seen in the
 // value atomicAdd returns) makes its thread move 0x8000 counts to the global image, and a CTA-wide barrier per two batches of
-// kSmemThreads x kSmemUnroll = 2048 rays bounds what the other threads can add in between (0x7FFF + 4096 < 0xFFFF; the
+// kSmemThreads x kSmemUnroll = 2560 rays bounds what the other threads can add in between (0x7FFF + 5120 < 0xFFFF; the
 // subtraction lands before the barrier, so every counter is <= 0x7FFF at every barrier).  The next batch's loads are issued
 // before the current batch is binned: the barrier does not drain the memory pipeline.
 // (Measured and rejected: the image split over the shared memories of a 2-CTA cluster, 32-bit counters, both CTAs reading
@@ -27,9 +27,13 @@
 
 namespace tt {
 
-static constexpr int kSmemThreads = 512;
+#ifndef TT_HIST_THREADS
+#define TT_HIST_THREADS 640      // measured 384 / 512 / 640 / 768 threads: 1.22 / 1.02 / 0.91 / 1.03 ms per 1e8 rays (92 registers at 640; 768 spills)
+#endif
+static constexpr int kSmemThreads = TT_HIST_THREADS;
 static constexpr int kSmemUnroll = 4;                        // rays per thread and batch
-static constexpr int kSmemChunk = kSmemThreads * kSmemUnroll;      // a batch = 2048 consecutive rays
+static_assert(2 * TT_HIST_THREADS * 4 < 0x8000, "the overflow protocol needs fewer than 0x8000 adds between two barriers");
+static constexpr int kSmemChunk = kSmemThreads * kSmemUnroll;      // a batch = 2560 consecutive rays
 
 // VEC: the four rows of rf_in are 16-byte aligned (even ray count): a thread loads its rays as two double2 per row
 template <bool VEC>
@@ -47,8 +51,8 @@ optics_hist_smem16_kernel(const double* __restrict__ rf_in, const double* __rest
     const double xlo = sx[0], xhi = sx[A.nbx], xs = (double)A.nbx / (xhi - xlo);
     const double ylo = sy[0], yhi = sy[A.nby], ys = (double)A.nby / (yhi - ylo);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    // batch `it` of this CTA = rays [c * 2048, (c + 1) * 2048), c = it * gridDim.x + blockIdx.x; the thread's rays in it:
-    // 2 t, 2 t + 1, 1024 + 2 t, 1024 + 2 t + 1 (constant offsets from one address per row)
+    // batch `it` of this CTA = rays [c * kSmemChunk, (c + 1) * kSmemChunk), c = it * gridDim.x + blockIdx.x; the thread's rays
+    // in it: 2 t, 2 t + 1, kSmemChunk / 2 + 2 t, kSmemChunk / 2 + 2 t + 1 (constant offsets from one address per row)
     double bufa[4][kSmemUnroll], bufb[4][kSmemUnroll];       // [row][ray]
 #define TT_HIST_LOAD(buf, it)                                                                                    \
     {                                                                                                            \
@@ -93,7 +97,7 @@ optics_hist_smem16_kernel(const double* __restrict__ rf_in, const double* __rest
         }                                                                                                        \
     }
     // two batches per turn, the buffers taking turns (no register copies); every thread makes the same number of turns
-    // (the barrier), batches behind the end of the rays are empty.  Adds between two barriers: 2 x 2048 < 0x8000.
+    // (the barrier), batches behind the end of the rays are empty.  Adds between two barriers: 2 x kSmemChunk = 5120 < 0x8000.
     TT_HIST_LOAD(bufa, 0L)
     for (long it = 0; it < niter; it += 2) {
         TT_HIST_LOAD(bufb, it + 1)

@@ -134,6 +134,13 @@ TT_HD void face_eval(const FaceQ& q, f32x2 tuv, f32x2& guv, float& gw) {
                                // instructions there (1.6 lanes active): 139.6 vs 134.8 warp-instructions per warp-step.
                                // Host-tested (tests/test_host_kernels.py builds either form), GPU suite green with it.
 #endif
+#ifndef TT_FACE_PREFETCH
+#define TT_FACE_PREFETCH 0     // experiment: planes beyond the register prefetch (k+2) whose face is pulled into L2
+                               // (prefetch.global.L2): at 1025^3 every fourth face load is a first touch served by DRAM
+#endif
+#if TT_FACE_PREFETCH && defined(__CUDA_ARCH__)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 #ifndef TT_FACE_FASTPATH
 #define TT_FACE_FASTPATH 1     // warp-uniform shortcut for whole-cell steps: when every lane of the warp starts ON its
                                // plane and no lane predicts a side crossing, the stage coefficients are the base face,
@@ -291,6 +298,12 @@ TT_HD unsigned face_ray_f32x2(const float4* __restrict__ faces, const double* __
             // face k+2, consumed at the end of the step.  Unconditional (a predicated load goes through temporaries and
             // 12 moves): the grid carries one spare plane behind the last face for the load issued in the last cell
             N = face_ldw(p + 2 * fplane);
+#if TT_FACE_PREFETCH && defined(__CUDA_ARCH__)
+            if (k + 2 + TT_FACE_PREFETCH <= nw) {
+                prefetch_l2(p + (2 + TT_FACE_PREFETCH) * fplane);
+                prefetch_l2(p + (2 + TT_FACE_PREFETCH) * fplane + 2);
+            }
+#endif
             // ---- stage 1 and the length of this step -------------------------------------------------------
             const float q = trcp<float>(dw);        // (dw > TT_MARCH_MIN_DW: checked at the entry and after every step)
             bool ok = true;

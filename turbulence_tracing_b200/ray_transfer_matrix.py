@@ -47,6 +47,9 @@ def _ops_angular_filter(Rs):
     return [_op(_lib.OP_ANNULAR_STOP, Rs[2 * i], Rs[2 * i + 1]) for i in range(len(Rs) // 2)]
 
 
+_kernel_events = None      # measurement aid (bench.py): a list collects the (start, end) CUDA events of every launch below
+
+
 def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True, weights=None, Hw=None):
     """Launch the fused kernel.  hist = (xedges_dev, yedges_dev, H_dev) or None; weights/Hw: optional
     per-ray weights and the FP64 image they are summed into."""
@@ -66,9 +69,17 @@ def _run(r_dev, program, pos_scale=1.0, perm=None, hist=None, want_rf=True, weig
     if hist is not None:
         xe, ye, H = hist
         nbx, nby = xe.numel() - 1, ye.numel() - 1
+    ev = _kernel_events
+    if ev is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.tt_optics_hist_weighted(_lib.ptr(r_dev), n, _lib.ptr(perm), float(pos_scale), prog, len(program),
                                            _lib.ptr(xe), nbx, _lib.ptr(ye), nby, _lib.ptr(H), _lib.ptr(weights),
                                            _lib.ptr(Hw), _lib.ptr(out), _lib.stream_ptr()), "tt_optics_hist")
+    if ev is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        ev.append((e0, e1))
     return out
 
 
