@@ -464,3 +464,50 @@ def test_fused_aux_grid_equals_the_elementwise_composition(tt, direction, dt):
             kap = cube.kappa().double().cpu().numpy().transpose(fa[2], fa[1], fa[0])
             assert np.isfinite(kap).all() and kap.max() > 0
             np.testing.assert_allclose(got[..., 3], kap, rtol=2e-7 if dt == "float32" else 1e-14, atol=0)
+
+
+def test_pageable_upload_through_the_staging_ring(tt, monkeypatch):
+    """tt_h2d_pageable (worker threads -> pinned ring -> one DMA per piece) delivers the bytes of a pageable array: sizes that
+    are not a multiple of the 4 MB piece, more pieces than ring slots (the slots are reused behind their DMA events), 1 / 3 /
+    default worker threads, two calls back to back on different streams; small and pinned sources take the plain copy."""
+    import torch
+    lib = tt._lib
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 2**62, size=(300 * (1 << 20) + 12345) // 8, dtype=np.int64)       # 300 MB + a ragged tail: 76 pieces > 32 slots
+    src = torch.from_numpy(a)
+    assert not src.is_pinned()
+    for threads in ("1", "3", None):
+        if threads is None:
+            monkeypatch.delenv("TT_H2D_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("TT_H2D_THREADS", threads)
+        dst = torch.zeros(a.shape, dtype=torch.int64, device="cuda")
+        lib.h2d(dst, src)
+        torch.cuda.synchronize()
+        assert torch.equal(dst.cpu(), src), threads
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    d1 = torch.zeros_like(dst)
+    d2 = torch.zeros(40 * (1 << 20) // 8, dtype=torch.int64, device="cuda")
+    with torch.cuda.stream(s1):
+        lib.h2d(d1, src)
+    with torch.cuda.stream(s2):
+        lib.h2d(d2, src[: d2.numel()])
+    torch.cuda.synchronize()
+    assert torch.equal(d1.cpu(), src) and torch.equal(d2.cpu(), src[: d2.numel()])
+    small = torch.arange(1000, dtype=torch.float64)
+    assert torch.equal(lib.h2d(None, small).cpu(), small)
+    pinned = src[:5_000_000].clone().pin_memory()
+    assert torch.equal(lib.h2d(None, pinned).cpu(), pinned)
+    # the solve() pipeline with plain numpy rays takes this path: the result equals that of device-resident rays
+    pt = tt.particle_tracker
+    x = np.linspace(-5e-3, 5e-3, 33)
+    cube = pt.ElectronCube(x, x, x, keep_sf=False, verbose=False)
+    cube.external_ne(1e25 * (1 + 0.2 * np.sin(600 * x)[:, None, None] * np.cos(500 * x)[None, :, None]) * np.ones((33, 33, 33)))
+    cube.calc_dndr()
+    cube.init_beam(6_000_000, 4e-3, 0.05e-3, seed=3)
+    s0_dev = cube.s0
+    rf_dev = np.asarray(cube.solve()).copy()
+    cube.s0 = np.asarray(s0_dev).copy()               # pageable numpy, 288 MB: rows of 48 MB each
+    cube.pipeline_first_rays = 100_000
+    rf_host = np.asarray(cube.solve())
+    np.testing.assert_array_equal(rf_host, rf_dev)

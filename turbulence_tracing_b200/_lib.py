@@ -69,6 +69,7 @@ PROTOTYPES = {
     "tt_trace_faces": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
                           _vp, _vp]),
+    "tt_h2d_pageable": (_i, [_vp, _vp, _sz, _vp]),
     "tt_build_aux_grid": (_i, [_vp, _i, _vp, _d, _vp, _d, _vp, _i, C.POINTER(_I3), _i, _d, _d, _d, _d, _i, _vp, _i, _vp]),
     "tt_calc_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp]),
     "tt_trace_axes": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -235,5 +236,24 @@ def to_device(a, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     if not t.is_cuda:
-        t = t.cuda(non_blocking=False)
+        t = h2d(None, t.contiguous())
     return t.contiguous()
+
+
+H2D_PAGEABLE_MIN = 8 << 20        # bytes from which a pageable source goes through tt_h2d_pageable
+
+
+def h2d(dst, src):
+    """Copy the contiguous CPU tensor ``src`` into the contiguous CUDA tensor ``dst`` (allocated here if None) on the
+    current stream.  Pinned sources: one asynchronous copy.  Big pageable sources (a drop-in caller's numpy arrays):
+    ``tt_h2d_pageable`` -- worker threads stage them through pinned buffers, several times the rate of the driver's own
+    single-threaded staging.  Returns ``dst``."""
+    torch = torch_cuda()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=src.dtype, device="cuda")
+    nbytes = src.numel() * src.element_size()
+    if nbytes < H2D_PAGEABLE_MIN or src.is_pinned() or not src.is_contiguous() or not dst.is_contiguous():
+        dst.copy_(src, non_blocking=True)
+    else:
+        check(load().tt_h2d_pageable(dst.data_ptr(), src.data_ptr(), nbytes, stream_ptr()), "tt_h2d_pageable")
+    return dst

@@ -120,15 +120,27 @@ def upload_cube_sharded(ne_host, device=None):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     rank, world = rank_world()
+    from . import _lib
+    on_gpu = torch.device(device).type == "cuda"
+
+    def up(dst, src):                    # pageable sources go through the staging threads of tt_h2d_pageable
+        if on_gpu:
+            with torch.cuda.device(dst.device):
+                _lib.h2d(dst, src)
+        else:
+            dst.copy_(src)
+
     if world == 1:
-        return torch.from_numpy(a).to(device, non_blocking=True)
+        out = torch.empty(a.shape, dtype=dt, device=device)
+        up(out.view(-1), torch.from_numpy(flat))
+        return out
     n = flat.size
     chunk = (n + world - 1) // world
     out = torch.empty(world * chunk, dtype=dt, device=device)
     lo, hi = min(rank * chunk, n), min((rank + 1) * chunk, n)
     mine = out[rank * chunk:(rank + 1) * chunk]
     if hi > lo:
-        mine[:hi - lo].copy_(torch.from_numpy(flat[lo:hi]), non_blocking=True)
+        up(mine[:hi - lo], torch.from_numpy(flat[lo:hi]))
     if hi - lo < chunk:
         mine[hi - lo:].zero_()
     _dist().all_gather_into_tensor(out, mine)          # in place: rank r's input is slice r of the output

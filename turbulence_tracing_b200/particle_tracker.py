@@ -590,8 +590,8 @@ class ElectronCube:
                     if ci == 0:
                         t_start = torch.cuda.Event(enable_timing=True)
                         t_start.record(copy)
-                    for r in range(6):
-                        s0b[r].copy_(src[r, lo:lo + n], non_blocking=True)
+                    for r in range(6):                     # (pageable source: staged by worker threads, _lib.h2d)
+                        _lib.h2d(s0b[r], src[r, lo:lo + n])
                     ready = torch.cuda.Event(enable_timing=(ci == 0))
                     ready.record(copy)
                 main.wait_event(ready)
