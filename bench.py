@@ -574,6 +574,7 @@ def gpu_measure(ctx, args, wl, *, rays_per_rank, first_ray, dtype, steps, warmup
                  "d2h_bytes_per_step": int(last2[0].numel() * 8 + 8), "gpu_launches": launches2,
                  "pipeline": {"chunk_cap_rays": getattr(cube2, "pipeline_chunk_rays", None) or "adaptive",
                               "first_chunk_upload_gbs": getattr(cube2, "last_upload_gbs", None),
+                              "best_chunk_upload_gbs": getattr(cube2, "last_upload_gbs_max", None),
                               "chunk_growth": getattr(cube2, "last_pipeline_growth", None)},
                  "cube_upload": "sharded: 1/N per rank over PCIe + one NCCL all-gather (distributed.upload_cube_sharded)" if world > 1 else "whole cube",
                  "api": "ElectronCube.external_ne/calc_dndr/solve + Shadowgraphy.solve/histogram, numpy in, H out"}

@@ -587,12 +587,11 @@ class ElectronCube:
                         bufs[b] = torch.empty((6, n), dtype=torch.float64, device="cuda")
                         bufs[b].record_stream(main)
                     s0b = bufs[b] if n == bufs[b].shape[1] else bufs[b].reshape(-1)[:6 * n].view(6, n)
-                    if ci == 0:
-                        t_start = torch.cuda.Event(enable_timing=True)
-                        t_start.record(copy)
+                    t_start = torch.cuda.Event(enable_timing=True)
+                    t_start.record(copy)
                     for r in range(6):                     # (pageable source: staged by worker threads, _lib.h2d)
                         _lib.h2d(s0b[r], src[r, lo:lo + n])
-                    ready = torch.cuda.Event(enable_timing=(ci == 0))
+                    ready = torch.cuda.Event(enable_timing=True)
                     ready.record(copy)
                 main.wait_event(ready)
                 rf_c, sf_c, st_c, ax_c = outputs(n)
@@ -607,27 +606,33 @@ class ElectronCube:
                     perm[lo:lo + n] = (pc + lo) if pc is not None else torch.arange(lo, lo + n, dtype=torch.int32, device="cuda")
                 free[b] = torch.cuda.Event()
                 free[b].record(main)
-                if growth is None:                         # after the first chunk: pick the schedule
-                    growth = float(growth_user) if growth_user else 0.0
-                    if not growth:
-                        ready.synchronize()                # ~1.5 ms; the GPU is busy tracing the first chunk meanwhile
-                        gbs = 48.0 * n / max(t_start.elapsed_time(ready), 1e-3) * 1e-6
+                # the schedule follows the measured upload rate of the chunk just sent (its copy is finished or about to
+                # be: the GPU still has the trace of this chunk queued, the host loses nothing by waiting for the event).
+                # Pinned sources: the rate is the link's and does not change; pageable sources are staged by worker threads
+                # and get faster with the size of a row (16 GB/s for the 12.5 MB rows of the first chunk, 48 GB/s beyond)
+                if growth_user:
+                    growth = float(growth_user)
+                else:
+                    ready.synchronize()
+                    gbs = 48.0 * n / max(t_start.elapsed_time(ready), 1e-3) * 1e-6
+                    if ci == 0:
                         self.last_upload_gbs = gbs
-                        # the upload of chunk i+1 hides behind the trace of chunk i as long as
-                        #   growth <= (trace time per ray) / (upload time per ray);
-                        # measured on an 8-GPU box, every rank uploading at ~20 GB/s: 2.4 ns per ray up, 3.0 ns per ray
-                        # traced (513 planes) -- doubling the chunk exposed 1.8 ns per ray of every growth step, 40 ms of
-                        # a 300 ms solve.  Trace time: 6.1 ps per ray-step in FP32 on a B200, twice that in FP64.
-                        up_ns = 48.0 / max(gbs, 1e-3)
-                        tr_ns = (self.shape[self._par] - 1) * self.steps_per_cell * (6.1e-3 if grid.dtype == torch.float32 else 1.8e-2)
-                        growth = min(3.0, max(1.0, 0.9 * tr_ns / up_ns))
-                        if growth < 1.1:                   # upload-bound anyway: equal chunks, not too small
-                            growth = 1.0
-                            jump = max(n, min(6_250_000, cap))
-                        if not cap_user:
-                            cap = 50_000_000 if gbs >= 35.0 else (25_000_000 if gbs >= 15.0 else 12_500_000)
-                    growth = max(growth, 1.0)
-                    self.last_pipeline_growth = growth
+                    self.last_upload_gbs_max = max(gbs, getattr(self, "last_upload_gbs_max", 0.0) if ci else 0.0)
+                    # the upload of chunk i+1 hides behind the trace of chunk i as long as
+                    #   growth <= (trace time per ray) / (upload time per ray);
+                    # measured on an 8-GPU box, every rank uploading at ~20 GB/s: 2.4 ns per ray up, 3.0 ns per ray
+                    # traced (513 planes) -- doubling the chunk exposed 1.8 ns per ray of every growth step, 40 ms of
+                    # a 300 ms solve.  Trace time: 6.1 ps per ray-step in FP32 on a B200, twice that in FP64.
+                    up_ns = 48.0 / max(gbs, 1e-3)
+                    tr_ns = (self.shape[self._par] - 1) * self.steps_per_cell * (6.1e-3 if grid.dtype == torch.float32 else 1.8e-2)
+                    growth = min(3.0, max(1.0, 0.9 * tr_ns / up_ns))
+                    jump = 0
+                    if growth < 1.1:                       # upload-bound anyway: equal chunks, not too small
+                        growth = 1.0
+                        jump = max(n, min(6_250_000, cap))
+                    if not cap_user:
+                        cap = 50_000_000 if gbs >= 35.0 else (25_000_000 if gbs >= 15.0 else 12_500_000)
+                self.last_pipeline_growth = growth
                 lo += n
                 ci += 1
                 n = min(max(int(growth * n), jump), cap)
