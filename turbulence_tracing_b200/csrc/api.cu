@@ -128,8 +128,9 @@ extern "C" int tt_solve_host(const double* ne_host, const int n_xyz[3], const do
     TT_CUDA(cnt.alloc(sizeof(unsigned long long)));
     TT_CUDA(status.alloc((size_t)np));
     cudaStream_t s = 0;
-    TT_CUDA(cudaMemcpyAsync(ne.p, ne_host, nvox * sizeof(double), cudaMemcpyHostToDevice, s));
-    TT_CUDA(cudaMemcpyAsync(s0.p, s0_host, (size_t)np * 6 * sizeof(double), cudaMemcpyHostToDevice, s));
+    // (pageable host buffers are staged by worker threads: tt_h2d_pageable, csrc/h2d.cu)
+    { int rc_ = tt_h2d_pageable(ne.p, ne_host, nvox * sizeof(double), (tt_stream_t)s); if (rc_) return rc_; }
+    { int rc_ = tt_h2d_pageable(s0.p, s0_host, (size_t)np * 6 * sizeof(double), (tt_stream_t)s); if (rc_) return rc_; }
     TT_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
     rc = tt_calc_dndr(ne.p, TT_F64, n_xyz, spacing_xyz, par, nc, ne_max, grid.p, dtype, s);
     if (rc) return rc;

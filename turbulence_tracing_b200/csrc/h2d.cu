@@ -70,7 +70,11 @@ extern "C" int tt_h2d_pageable(void* dst_dev, const void* src_host, size_t bytes
     if (e != cudaSuccess) return cuda_fail(e, "tt_h2d_pageable: cudaGetDevice");
     TT_REQUIRE(dev >= 0 && dev < 64, "tt_h2d_pageable: device index %d out of range", dev);
     cudaStream_t s = (cudaStream_t)stream;
-    if (bytes < 2 * kPiece) {                      // small: the driver's own staging is as good
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    (void)cudaGetLastError();                      // (an unregistered pointer is not an error here)
+    if (bytes < 2 * kPiece || pinned) {            // small, or already page-locked: one plain (asynchronous) copy
         e = cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, s);
         return e == cudaSuccess ? TT_OK : cuda_fail(e, "tt_h2d_pageable: cudaMemcpyAsync");
     }
