@@ -39,5 +39,25 @@ cube.external_B(B); cube.external_Te(torch.full((M, M, M), 100.0, device="cuda")
 cube.calc_dndr()
 cube.init_beam(5000, 4e-3, 1e-3, seed=4)
 cube.solve()
+# round 2, session 3: the privatised detector kernel (>= 65536 rays in storage order; even and odd counts = double2 / scalar
+# loads; a focused bundle that overflows the 16-bit counters), the fused aux grid with cubes for Te and Z in FP32 and
+# FP64, the staged upload of a pageable array (more pieces than ring slots)
+rng = np.random.default_rng(1)
+for n in (70_000, 70_001):
+    r0 = np.zeros((4, n)); r0[0] = rng.uniform(-10e-3, 10e-3, n); r0[2] = rng.uniform(-7e-3, 7e-3, n); r0[1, ::7] = np.nan
+    sh = rtm.Shadowgraphy(r0); sh.solve(); sh.histogram()
+    tot += sh.H.sum()
+r0 = np.zeros((4, 5_200_000)); r0[0] = 1e-4; r0[2] = 2e-4
+sh = rtm.Shadowgraphy(r0); sh.solve(); sh.histogram()
+assert sh.H.max() == 5_200_000
+for dt in (torch.float32, torch.float64):
+    c2 = pt.ElectronCube(x, x, x, "y", B_on=True, inv_brems=True, phaseshift=True, verbose=False, dtype=str(dt).replace("torch.", ""))
+    c2.external_ne(ne.to(dt)); c2.external_B(B.to(dt)); c2.external_Te(torch.full((M, M, M), 80.0, device="cuda", dtype=dt))
+    c2.external_Z(torch.full((M, M, M), 2.0, device="cuda", dtype=dt)); c2.calc_dndr(); c2.set_up_interps()
+from turbulence_tracing_b200 import _lib
+a = torch.from_numpy(rng.integers(0, 1 << 40, size=(150 << 20) // 8 + 3))
+d = _lib.h2d(None, a)
+torch.cuda.synchronize()
+assert torch.equal(d.cpu(), a)
 torch.cuda.synchronize()
 print("sanitizer target done", M, int(tot))
