@@ -69,6 +69,16 @@ def test_argument_errors_are_codes_not_exceptions(lib):
     prog[0].op = 99
     assert lib.tt_optics_hist(C.c_void_p(8), 10, 1.0, prog, 1, None, 0, None, 0, None, C.c_void_p(8), None) == 1
     assert b"unknown op" in lib.tt_last_error()
+    # round 2: staged upload and aux-grid builder
+    assert lib.tt_h2d_pageable(None, None, 0, None) == 0                      # nothing to copy
+    assert lib.tt_h2d_pageable(None, C.c_void_p(8), 16, None) == 1 and b"null" in lib.tt_last_error()
+    nan = float("nan")
+    assert lib.tt_build_aux_grid(C.c_void_p(8), 0, None, 100.0, None, 1.0, None, 0, n, 2, 1e27, 1.0, 1e15, nan, 0,
+                                 C.c_void_p(8), 0, None) == 1 and b"nothing to build" in lib.tt_last_error()
+    assert lib.tt_build_aux_grid(C.c_void_p(8), 0, None, 0.0, None, 1.0, None, 0, n, 2, 1e27, 1.0, 1e15, nan, 1,
+                                 C.c_void_p(8), 0, None) == 1 and b"Te" in lib.tt_last_error()
+    assert lib.tt_build_aux_grid(C.c_void_p(8), 7, None, 100.0, None, 1.0, None, 0, n, 2, 1e27, 1.0, 1e15, nan, 1,
+                                 C.c_void_p(8), 0, None) == 1 and b"dtype" in lib.tt_last_error()
 
 
 def test_no_gpu_means_loud_failure_not_fallback(lib):
