@@ -18,7 +18,6 @@ VARIANTS = {
     "base": ["-DTT_EVENT_PACK_W=0", "-DTT_EVENT_LD3=0"],
     "nomerge": ["-DTT_EVENT_MERGE=0"],
     "nofastdiv": ["-DTT_EVENT_FASTDIV=0"],
-    "lean": ["-DTT_EVENT_LEAN=1"],
     "b64": ["-DTT_EVENT_BLOCK=64", "-DTT_EVENT_MIN_BLOCKS=10"],
     "b256": ["-DTT_EVENT_BLOCK=256", "-DTT_EVENT_MIN_BLOCKS=2"],
     "mb6": ["-DTT_EVENT_MIN_BLOCKS=6"],
@@ -59,7 +58,8 @@ def main():
     other = {"h_t640": ("optics_hist.cu", ["-DTT_HIST_THREADS=640"]), "h_t768": ("optics_hist.cu", ["-DTT_HIST_THREADS=768"]),
              "h_t384": ("optics_hist.cu", ["-DTT_HIST_THREADS=384"]), "h_new": ("optics_hist.cu", []),
              "a_mb2": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=2"]), "a_mb4": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=4"]),
-             "a_new": ("trace_event.cu", [])}
+             "a_new": ("trace_event.cu", []),
+             "x_new": ("trace_axes.cu", [])}       # (e_lean / x_rcp: measured in round 2 -- rejected / adopted, macros removed)
     by_file = {t: ("trace_face.cu", f) for t, f in FACE_VARIANTS.items()}
     by_file.update(other)
     for tag, (src, flags) in by_file.items():

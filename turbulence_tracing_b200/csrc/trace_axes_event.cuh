@@ -38,11 +38,9 @@ TT_HD int find_cell(const double* __restrict__ ax, int n, double x) {
 // the FP64 gather kernel of trace_axes.cu stays the second pass for everything unusual (launched outside the cube beside
 // the entry face, steep / backward, side exit, possible time cap, non-finite): those rays are flagged
 // TT_RAY_DEFERRED and redone from s0.
-#ifndef TT_AXES_RCP
-#define TT_AXES_RCP 0              // experiment prepared for round 2, NOT measured yet: keep 1/h_u, 1/h_v of the current cell
-                                   // (refreshed at u / v crossings only) so that a plane arrival costs two multiplications
-                                   // instead of two divisions (the FP32 kernel has the XU pipe at 18 %); host-tested
-#endif
+// 1/h_u, 1/h_v of the current cell are kept as state (refreshed at u / v crossings only): a plane arrival costs two
+// multiplications instead of two divisions (measured on B200, stretched 257^3 mesh, 1e7 rays: float4 grid 34.2 -> 31.0 ms,
+// double4 grid 62.1 -> 55.9 ms; same accuracy on the fixtures, profiles/r02_ab_lean_axesrcp.txt)
 // Returns the (sub-)plane arrivals of this ray (0 if deferred).
 template <typename T>
 TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, const double* __restrict__ s0, long ray,
@@ -86,12 +84,8 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
         }
     }
     R du = D[0], dv = D[1], dw = D[2], s = 0;
-#if TT_AXES_RCP
     R ihu = R(1) / hu, ihv = R(1) / hv;
     R ru = hw * ihu, rv = hw * ihv;
-#else
-    R ru = hw / hu, rv = hw / hv;
-#endif
     const int spc = A.spc;
     const R hsub = R(1) / (R)spc;
     int j = (int)(fw * (R)spc);               // current sub-plane interval of the w-cell
@@ -170,11 +164,7 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
                     if (++k >= nw - 1) break;                                 // far face: done
                     p += plane;
                     hw = ldg_f64(axw + k + 1) - ldg_f64(axw + k);
-#if TT_AXES_RCP
                     ru = hw * ihu; rv = hw * ihv;
-#else
-                    ru = hw / hu; rv = hw / hv;
-#endif
                     load_cell();
                 }
             } else {
@@ -189,21 +179,13 @@ TT_HD unsigned axes_event_ray(const typename GridT<T>::V4* __restrict__ grid, co
                     const R hn = ldg_f64(axu + cu + 1) - xu0, sc = hu / hn;
                     tu = cross == 1 ? (tu - R(1)) * sc : fma(tu, sc, R(1));
                     hu = hn;
-#if TT_AXES_RCP
                     ihu = R(1) / hu; ru = hw * ihu;
-#else
-                    ru = hw / hu;
-#endif
                 } else {
                     xv0 = ldg_f64(axv + cv);
                     const R hn = ldg_f64(axv + cv + 1) - xv0, sc = hv / hn;
                     tv = cross == 2 ? (tv - R(1)) * sc : fma(tv, sc, R(1));
                     hv = hn;
-#if TT_AXES_RCP
                     ihv = R(1) / hv; rv = hw * ihv;
-#else
-                    rv = hw / hv;
-#endif
                 }
                 load_cell();
             }

@@ -16,11 +16,9 @@ namespace tt {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-#ifndef TT_EVENT_LEAN
-#define TT_EVENT_LEAN 0            // (packed kernel) experiment prepared for round 2, NOT measured yet: the prefetch of plane
-                                   // k+2 issued where the cell changes instead of behind a flag at the loop top -- same
-                                   // loads, same results (host-tested bit-identical), a few control instructions less
-#endif
+// (Measured and removed in round 2: issuing the prefetch of plane k+2 where the cell changes instead of behind the `have_next`
+// flag at the loop top -- same loads, bit-identical rays, a few control instructions less: 391.5 vs 383.0 ms on 513^3 / 1e8
+// rays through tt_trace, 62.1 vs 62.0 ms on configs[3]; profiles/r02_ab_lean_axesrcp.txt.)
 #ifndef TT_EVENT_MERGE
 #define TT_EVENT_MERGE 1           // a cell change (next plane OR a u / v face) renews the polynomial in two halves: the base
                                    // plane (advance: base += primed; face: 4 corners of the new column) and, in code COMMON
@@ -468,17 +466,6 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
             }
         };
         load_cell();
-#if TT_EVENT_LEAN
-        // corners of plane k+2, loaded right after the cell changes instead of behind a flag test at the loop top
-        auto load_next = [&]() {
-            if (k + 2 <= nw - 1) {
-                const float4* p2 = p + 2 * plane;
-                n00 = TT_LDN(p2); n10 = TT_LDN(p2 + 1); n01 = TT_LDN(p2 + nu); n11 = TT_LDN(p2 + nu + 1);
-            }
-        };
-        load_next();
-        while (true) {
-#else
         bool have_next = false;
         while (true) {
             if (!have_next && k + 2 <= nw - 1) {
@@ -486,7 +473,6 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 n00 = TT_LDN(p2); n10 = TT_LDN(p2 + 1); n01 = TT_LDN(p2 + nu); n11 = TT_LDN(p2 + nu + 1);
                 have_next = true;
             }
-#endif
             // ---- stage 1 and the length of this step -------------------------------------------
             T q = trcp<T>(dw), hq = hw * q;
             bool ok = dw > T(TT_MARCH_MIN_DW);
@@ -647,11 +633,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                     tri2_primed(bxy, TT_XY(b00), TT_XY(b10), TT_XY(b01), TT_XY(b11));
                     tri2_primed(bzk, TT_ZW(b00), TT_ZW(b10), TT_ZW(b01), TT_ZW(b11));
                 }
-#if TT_EVENT_LEAN
-                load_next();
-#else
                 have_next = false;
-#endif
             }
 #else
             if (cross == 0) {
@@ -677,11 +659,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                         tri2_advance(bxy, TT_XY(b00), TT_XY(b10), TT_XY(b01), TT_XY(b11));
                         tri2_advance(bzk, TT_ZW(b00), TT_ZW(b10), TT_ZW(b01), TT_ZW(b11));
                     }
-#if TT_EVENT_LEAN
-                    load_next();
-#else
                     have_next = false;
-#endif
                 }
             } else {
                 fw += h;
@@ -694,11 +672,7 @@ TT_HD unsigned event_ray_f32x2(const float4* __restrict__ grid, const double* __
                 tuv = pk2(tu, tv);
                 if (cu < 0 || cu > nu - 2 || cv < 0 || cv > nv - 2) { fast = false; break; }
                 load_cell();
-#if TT_EVENT_LEAN
-                load_next();
-#else
                 have_next = false;
-#endif
             }
 #endif
         }
