@@ -284,6 +284,7 @@ TRACE_KERNELS = {       # (mangled-name substring, display name) of the kernel t
     ("float32", False, True): ("trace_face_kernel_f32x2ILb0", "trace_face_kernel_f32x2<false>"),
     ("float32", False, False): ("trace_event_kernel_f32x2ILb1ELb0ELb1ELb0", "trace_event_kernel_f32x2<1,0,1,0>"),
     ("float32", True, False): ("trace_event_kernel_f32x2ILb1ELb1ELb1ELb1", "trace_event_kernel_f32x2<1,1,1,1>"),
+    ("float32", True, True): ("trace_face_aux_kernel_f32x2ILb0", "trace_face_aux_kernel_f32x2<false>"),
     ("float64", False, False): ("trace_event_kernelIdLb1", "trace_event_kernel<double,true>"),
 }
 
@@ -627,7 +628,9 @@ def run_gpu_arm(args, wl):
     faces = main["faces"]
     key = f"{wl}/{dtype}/" + ("faces" if faces else str(args.variant or 3))
     kern = TRACE_KERNELS.get((dtype, aux, faces), ("", "trace kernel"))
-    if faces:
+    if faces and aux:
+        bps, note = 128, "one cell face of both coefficient grids per ray-step: 3 + 5 words of 16 B (gradient; ne/nc, B, kappa)"
+    elif faces:
         bps, note = 48, "one cell face = 3 x 16 B of bilinear coefficients per ray-step (SURVEY 8d counted 4 stages x 8 corners x 16 B = 512 B for a per-stage gather)"
     else:
         bps = 64 * (2 if dtype == "float64" else 1) * (2 if aux else 1)

@@ -170,6 +170,20 @@ int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* g
                  double* rf_dev, double* sf_dev, double* aux_out_dev,
                  unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
 
+/* tt_trace_aux in TT_F32 at 1 step per cell over FACE-coefficient grids (the production form of this extension, as
+ * tt_trace_faces is for tt_trace): next to the gradient faces of tt_build_face_grid a second grid holds, per cell face,
+ * the bilinear coefficients of ne/nc, B_u, B_v, B_w and kappa (five 16-byte words = 80 B per face cell,
+ * tt_face_aux_grid_bytes), formed once by tt_build_face_aux_grid from grid4_dev and aux4_dev (nullable: phase only).
+ * Same arguments, outputs, flags and ray order as tt_trace_aux; rays the event kernel cannot march are redone by the
+ * general kernel over grid4_dev / aux4_dev.  Same evidence upstream (call sites only): parity unpinned.              */
+size_t tt_face_aux_grid_bytes(const int n_xyz[3], int par);
+int tt_build_face_aux_grid(const void* grid4_dev, const void* aux4_dev, const int n_xyz[3], const double spacing_xyz[3],
+                           int par, void* faces_aux_dev, tt_stream_t stream);
+int tt_trace_faces_aux(const tt_trace_params* p, const tt_aux_params* a, const void* grid4_dev, const void* aux4_dev,
+                       const void* faces_dev, const void* faces_aux_dev, const double* s0_dev, long np,
+                       const uint32_t* perm_dev, double* rf_dev, double* sf_dev, double* aux_out_dev,
+                       unsigned long long* ray_steps_dev, uint8_t* status_dev, tt_stream_t stream);
+
 /* The aux4_dev grid of tt_trace_aux from the user's cubes in one pass: (B_u, B_v, B_w, kappa) per node in the gradient
  * grid's layout and dtype (grid_dtype).  Reference: only the call sites exist upstream (example_kitchensink.py:72-101:
  * external_B / external_Te / external_Z, B_on / inv_brems); the formula is the NRL-formulary inverse-bremsstrahlung

@@ -59,7 +59,10 @@ def main():
              "h_t384": ("optics_hist.cu", ["-DTT_HIST_THREADS=384"]), "h_new": ("optics_hist.cu", []),
              "a_mb2": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=2"]), "a_mb4": ("trace_event.cu", ["-DTT_EVENT_MIN_BLOCKS_AUX=4"]),
              "a_new": ("trace_event.cu", []),
-             "x_new": ("trace_axes.cu", [])}       # (e_lean / x_rcp: measured in round 2 -- rejected / adopted, macros removed)
+             "x_new": ("trace_axes.cu", []),
+             "fa_new": ("trace_face_aux.cu", []), "fa_mb2": ("trace_face_aux.cu", ["-DTT_FACE_AUX_MIN_BLOCKS=2"]),
+             "fa_b64": ("trace_face_aux.cu", ["-DTT_FACE_AUX_BLOCK=64", "-DTT_FACE_AUX_MIN_BLOCKS=6"]),
+             "fa_mb4": ("trace_face_aux.cu", ["-DTT_FACE_AUX_MIN_BLOCKS=4"])}       # (e_lean / x_rcp: measured in round 2 -- rejected / adopted, macros removed)
     by_file = {t: ("trace_face.cu", f) for t, f in FACE_VARIANTS.items()}
     by_file.update(other)
     for tag, (src, flags) in by_file.items():

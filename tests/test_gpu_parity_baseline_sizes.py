@@ -198,10 +198,13 @@ def test_c5_cube_1025_offsets_steps_and_sub_volume_oracle(tt):
     assert p <= 1e-5 * BEAM and a <= 1e-5
 
 
-def test_c4_packed_aux_kernel_at_257(tt):
-    """BASELINE configs[3] at its size (257^3 ne + B + Te, as bench.py --workload c4 builds them): the packed FP32x2
-    event kernel with phase / Faraday rotation / absorption on board against the FP64 gather kernel, and a uniform
-    plasma of the same size against the closed forms.  (Parity unpinned: the reference has call sites only.)"""
+@pytest.mark.parametrize("face_grid", ["auto", False])
+def test_c4_packed_aux_kernel_at_257(tt, face_grid):
+    """BASELINE configs[3] at its size (257^3 ne + B + Te, as bench.py --workload c4 builds them): the FP32 event kernels
+    with phase / Faraday rotation / absorption on board -- the face-coefficient kernel (tt_trace_faces_aux, the production
+    path, face_grid="auto") and the packed corner-grid kernel (tt_trace_aux, face_grid=False) -- against the FP64 gather
+    kernel, and a uniform plasma of the same size against the closed forms.  (Parity unpinned: the reference has call sites
+    only.)"""
     import torch
     pt = tt.particle_tracker
     M = 257
@@ -216,11 +219,12 @@ def test_c4_packed_aux_kernel_at_257(tt):
     out = {}
     for dtype, spc in (("float32", 1), ("float64", 2)):
         cube = pt.ElectronCube(x, x, x, B_on=True, inv_brems=True, phaseshift=True, dtype=dtype, steps_per_cell=spc,
-                               verbose=False)
+                               verbose=False, face_grid=face_grid)
         cube.external_ne(ne); cube.external_B(B); cube.external_Te(Te); cube.external_Z(1.0)
         cube.calc_dndr()
         cube.init_beam(200_000, BEAM, DIV, seed=8)
         rf = np.asarray(cube.solve())
+        assert (cube._faces_aux is not None) == (dtype == "float32" and face_grid == "auto")
         out[dtype] = (rf, np.asarray(cube.amp), np.asarray(cube.phase), np.asarray(cube.pol), np.asarray(cube.status))
     a, b = out["float32"], out["float64"]
     assert np.all(a[4] == 1)                           # all on the packed event kernel
@@ -238,7 +242,7 @@ def test_c4_packed_aux_kernel_at_257(tt):
     B_u = torch.zeros((M, M, M, 3), dtype=torch.float32, device="cuda")
     B_u[..., 0], B_u[..., 1], B_u[..., 2] = 0.3, -0.2, 10.0
     Te_u = torch.full((M, M, M), 100.0, dtype=torch.float32, device="cuda")
-    cube = pt.ElectronCube(x, x, x, B_on=True, inv_brems=True, phaseshift=True, dtype="float32", verbose=False)
+    cube = pt.ElectronCube(x, x, x, B_on=True, inv_brems=True, phaseshift=True, dtype="float32", verbose=False, face_grid=face_grid)
     cube.external_ne(ne_u); cube.external_B(B_u); cube.external_Te(Te_u); cube.external_Z(1.0)
     cube.calc_dndr()
     np.random.seed(2)

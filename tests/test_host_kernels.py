@@ -1015,3 +1015,106 @@ def test_face_kernel_body_non_cubic_cells_and_deferred_rays(face_lib, packed_lib
     c = _run_faces(face_lib, G2, xx, yy, zz, par, 5e-3, s1)
     assert not np.any(c[2] == DEFERRED)
     np.testing.assert_array_equal(c[0][:, m], a[0][:, m])
+
+
+# ------------------------------------------------------------------------- face-coefficient kernel with passive quantities
+@pytest.fixture(scope="module")
+def face_aux_lib(tmp_path_factory):
+    lib = _build_host(tmp_path_factory, "trace_face_aux_host")
+    vp = C.c_void_p
+    lib.host_trace_faces_aux.argtypes = [vp, vp, C.POINTER(C.c_int * 3), C.POINTER(C.c_double * 3), C.POINTER(C.c_double * 3), C.c_int,
+                                         C.c_double, C.c_double, vp, C.c_long, vp, vp, vp, vp, C.POINTER(C.c_ulonglong),
+                                         C.POINTER(C.c_long), C.c_double, C.c_double, vp, vp]
+    lib.host_trace_faces_aux.restype = C.c_int
+    return lib
+
+
+def _run_faces_aux(lib, G, aux4, x, y, z, par, extent, s0, omega_over_c, verdet_nc, want_sf=True):
+    n = s0.shape[1]
+    s0 = np.ascontiguousarray(s0, dtype=np.float64)
+    rf, sf, aux_out = np.full((4, n), np.nan), np.full((6, n), np.nan), np.full((3, n), np.nan)
+    status = np.zeros(n, dtype=np.uint8)
+    steps, nd = C.c_ulonglong(), C.c_long()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    dims = (C.c_int * 3)(len(x), len(y), len(z))
+    org = (C.c_double * 3)(x[0], y[0], z[0])
+    h = (C.c_double * 3)(*[(a[-1] - a[0]) / (len(a) - 1) for a in (x, y, z)])
+    nw, nv, nu = G.shape[:3]
+    faces = np.full((nw + 1, nv - 1, nu - 1, 12), np.nan, dtype=np.float32)
+    facesA = np.full((nw + 1, nv - 1, nu - 1, 20), np.nan, dtype=np.float32)
+    rc = lib.host_trace_faces_aux(p(G), p(aux4) if aux4 is not None else None, C.byref(dims), C.byref(org), C.byref(h), par,
+                                  float(extent), float(np.sqrt(8.0) * extent), p(s0), n, p(rf), p(sf) if want_sf else None,
+                                  p(aux_out), p(status), C.byref(steps), C.byref(nd), float(omega_over_c), float(verdet_nc),
+                                  p(faces), p(facesA))
+    assert rc == 0 and np.isfinite(facesA).all()
+    return rf, sf, status, steps.value, nd.value, aux_out, facesA
+
+
+def test_face_aux_kernel_body_on_the_host(face_aux_lib, face_lib, packed_lib, golden):
+    """face_aux_ray_f32x2 -- the face-coefficient kernel with phase / Faraday rotation / absorption on board -- on the host:
+    the same trajectories as the plain face kernel (to FP32 rounding: the step arithmetic is that of its rebase form), the
+    passive quantities within the tolerances of the packed corner-grid kernel against the independent scipy integration
+    (parity unpinned: only call sites upstream), agreement with that kernel to FP32 rounding, phase-only mode (no B / kappa
+    grid), and -- non-cubic cells, every probing direction, a wide divergent beam -- the same rays handed over."""
+    from oracle import ref_numpy as orc
+    g = golden("trace_grf33")
+    x, ne = g["x"], g["ne"]
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    B = np.zeros(ne.shape + (3,))
+    B[..., 2] = 10.0 + 3.0 * np.sin(400 * X) * np.cos(300 * Y)
+    B[..., 0] = 2.0 * np.cos(500 * Z + 200 * Y)
+    B[..., 1] = 1.5 * np.sin(350 * X - 250 * Z)
+    kappa = 40.0 * (1 + 0.5 * np.sin(600 * X) * np.sin(450 * Z)) * (ne / ne.max())
+    s0 = g["s0"][:, :12]
+    lwl = 1053e-9
+    d = orc_c.calc_dndr(ne, x, x, x, lwl)
+    rf_ref, amp, phase, rot = orc.solve_aux(ne, B, kappa, x, x, x, s0, float(g["extent"]), "z", lwl=lwl, batch=12)
+    aux4 = np.empty(ne.shape[::-1] + (4,), dtype=np.float32)
+    for k in range(3):
+        aux4[..., k] = B[..., k].transpose(2, 1, 0)
+    aux4[..., 3] = kappa.transpose(2, 1, 0)
+    aux4 = np.ascontiguousarray(aux4)
+    G = _grid4(ne, x, x, x, 2, np.float32)
+    V = orc.VERDET * lwl**2
+    ooc, vnc = d["omega"] / C_LIGHT, V * d["nc"]
+    a = _run_faces_aux(face_aux_lib, G, aux4, x, x, x, 2, float(g["extent"]), s0, ooc, vnc)
+    b = _run_packed(packed_lib, G, x, x, x, 2, float(g["extent"]), s0, 1, aux4=aux4, omega_over_c=ooc, verdet_nc=vnc)
+    f = _run_faces(face_lib, G, x, x, x, 2, float(g["extent"]), s0)
+    assert a[4] == 0 and np.all(a[2] == EXIT_FACE) and a[3] == 32 * 12
+    # trajectories: the plain face kernel's (rebase form vs vote form: FP32 rounding)
+    assert np.abs(a[0][0::2] - f[0][0::2]).max() <= 2e-4 * 52.3e-6 and np.abs(a[0][1::2] - f[0][1::2]).max() <= 2e-7
+    assert np.abs(a[1] - f[1])[:3].max() <= 1e-7
+    aux, auxb = a[5], b[5]
+    print(f"face aux kernel on the host (1 step per cell): phase {np.abs(aux[1] - phase).max():.2e} rad of {np.abs(phase).max():.0f}, "
+          f"rotation {np.abs(aux[2] - rot).max() / np.abs(rot).max():.1e} (rel), amplitude {np.abs(aux[0] - amp).max():.1e}; "
+          f"vs the corner-grid kernel: {np.abs(aux[1] - auxb[1]).max():.1e} rad, {np.abs(aux[2] - auxb[2]).max() / np.abs(rot).max():.1e}, "
+          f"{np.abs(aux[0] - auxb[0]).max():.1e}")
+    # the corner-grid kernel at the same 1 step per cell is the yardstick (the 4-step figures of the test above are tighter)
+    for i, scale in ((1, np.abs(phase).max()), (2, np.abs(rot).max()), (0, 1.0)):
+        ref_i = (amp, phase, rot)[i]
+        assert np.abs(aux[i] - ref_i).max() <= 1.5 * np.abs(auxb[i] - ref_i).max() + 2e-6 * scale
+        assert np.abs(aux[i] - auxb[i]).max() <= 2e-6 * scale
+    # phase only: no (B, kappa) grid
+    a0 = _run_faces_aux(face_aux_lib, G, None, x, x, x, 2, float(g["extent"]), s0, ooc, vnc, want_sf=False)
+    np.testing.assert_array_equal(a0[0], a[0])
+    np.testing.assert_array_equal(a0[5][1], aux[1])
+    assert np.all(a0[5][0] == 1.0) and not a0[5][2].any()
+    # non-cubic cells, every probing direction, wide divergent beam
+    xx, yy, zz = np.linspace(-5e-3, 5e-3, 41), np.linspace(-5e-3, 5e-3, 57), np.linspace(-5e-3, 5e-3, 33)
+    ne2 = orc.density("exponential_cos", xx, yy, zz, n_e0=3e24, Ly=2e-3, s=4e-3)
+    rng = np.random.default_rng(3)
+    for direction, par in (("x", 0), ("y", 1), ("z", 2)):
+        np.random.seed(6)
+        s1 = orc.init_beam(512, 5.2e-3, 2e-2, 5e-3, direction)
+        G2 = _grid4(ne2, xx, yy, zz, par, np.float32)
+        aux2 = rng.standard_normal(G2.shape).astype(np.float32)
+        aux2[..., 3] = np.abs(aux2[..., 3]) * 30
+        a = _run_faces_aux(face_aux_lib, G2, aux2, xx, yy, zz, par, 5e-3, s1, ooc, vnc)
+        b = _run_packed(packed_lib, G2, xx, yy, zz, par, 5e-3, s1, 1, aux4=aux2, omega_over_c=ooc, verdet_nc=vnc)
+        assert 0 < a[4] < s1.shape[1]
+        np.testing.assert_array_equal(a[2] == DEFERRED, b[2] == DEFERRED)
+        m = a[2] == EXIT_FACE
+        assert np.abs(a[0][:, m][0::2] - b[0][:, m][0::2]).max() <= 2e-4 * 52.3e-6
+        for i in range(3):
+            sc = max(np.abs(b[5][i][m]).max(), 1e-30)
+            assert np.abs(a[5][i][m] - b[5][i][m]).max() <= 5e-6 * sc, (direction, i)

@@ -69,6 +69,10 @@ PROTOTYPES = {
     "tt_trace_faces": (_i, [C.POINTER(TraceParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_trace_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp,
                           _vp, _vp]),
+    "tt_face_aux_grid_bytes": (_sz, [C.POINTER(_I3), _i]),
+    "tt_build_face_aux_grid": (_i, [_vp, _vp, C.POINTER(_I3), C.POINTER(_D3), _i, _vp, _vp]),
+    "tt_trace_faces_aux": (_i, [C.POINTER(TraceParams), C.POINTER(AuxParams), _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp,
+                                _vp, _vp, _vp]),
     "tt_h2d_pageable": (_i, [_vp, _vp, _sz, _vp]),
     "tt_build_aux_grid": (_i, [_vp, _i, _vp, _d, _vp, _d, _vp, _i, C.POINTER(_I3), _i, _d, _d, _d, _d, _i, _vp, _i, _vp]),
     "tt_calc_dndr_axes": (_i, [_vp, _i, C.POINTER(_I3), _vp, _vp, _vp, _i, _d, _d, _vp, _i, _vp]),

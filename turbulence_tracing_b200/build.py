@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "libtt_b200.so")
-SOURCES = ["api.cu", "h2d.cu", "calc_dndr.cu", "aux_grid.cu", "trace.cu", "trace_event.cu", "trace_face.cu", "trace_axes.cu", "rays.cu", "optics_hist.cu", "grf.cu", "spectrum.cu"]
+SOURCES = ["api.cu", "h2d.cu", "calc_dndr.cu", "aux_grid.cu", "trace.cu", "trace_event.cu", "trace_face.cu", "trace_face_aux.cu", "trace_axes.cu", "rays.cu", "optics_hist.cu", "grf.cu", "spectrum.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

@@ -212,6 +212,20 @@ extern "C" int tt_trace(const tt_trace_params* p, const void* grid4_dev, const d
     return launch_check("trace_kernel");
 }
 
+namespace tt {
+// the general kernel with the passive quantities over the rays an event kernel flagged TT_RAY_DEFERRED (FP32 grids)
+int launch_trace_aux_second_pass(const void* grid4, const void* aux4, const double* s0, const uint32_t* perm, double* rf, double* sf,
+                                 double* aux_out, unsigned long long* ray_steps, uint8_t* status, const TraceArgs& A,
+                                 const AuxArgs& AX, cudaStream_t s) {
+    const int block = 128;
+    const long blocks = (A.np + block - 1) / block;
+    const long blocks2 = blocks > 148 * 32 ? 148 * 32 : blocks;
+    trace_kernel<float, 1, true><<<(unsigned)blocks2, block, 0, s>>>((const float4*)grid4, s0, perm, rf, sf, ray_steps, status, A, 1,
+                                                                     (const float4*)aux4, aux_out, AX);
+    return launch_check("trace_kernel<aux>");
+}
+}  // namespace tt
+
 extern "C" int tt_trace_aux(const tt_trace_params* p, const tt_aux_params* a, const void* grid4_dev,
                             const void* aux4_dev, const double* s0_dev, long np, const uint32_t* perm_dev,
                             double* rf_dev, double* sf_dev, double* aux_out_dev, unsigned long long* ray_steps_dev,

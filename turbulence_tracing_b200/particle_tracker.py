@@ -114,6 +114,8 @@ class ElectronCube:
         self.face_grid = face_grid
         self._faces = None
         self._faces_valid = False
+        self._faces_aux = None
+        self._faces_aux_key = None
         self._nodes = None       # device node coordinates (x, y, z) when the axes are not uniformly spaced
         self._s0 = None
         self.ray_steps = 0       # RK4 steps taken inside the cube by the last solve()
@@ -288,6 +290,7 @@ class ElectronCube:
                                          int(bool(self.inv_brems)), _lib.ptr(a), _lib.dtype_code(grid.dtype),
                                          _lib.stream_ptr()), "tt_build_aux_grid")
         self._aux = a
+        self._faces_aux_key = None          # (the face coefficients of the passive fields follow)
         return a
 
     @property
@@ -368,6 +371,26 @@ class ElectronCube:
                                           _lib.ptr(self._faces), _lib.stream_ptr()), "tt_build_face_grid")
         self._faces_valid = True
         return self._faces
+
+    def _face_aux_grid(self, aux4):
+        """The second face-coefficient grid (ne/nc, B, kappa per cell face; 80 B per face cell) for the passive quantities,
+        built with the gradient faces; None when ``face_grid="auto"`` and it does not fit."""
+        torch = _lib.torch_cuda()
+        lib = _lib.load()
+        key = (None if aux4 is None else aux4.data_ptr(), self._grid.data_ptr())
+        if getattr(self, "_faces_aux", None) is not None and self._faces_aux_key == key and self._faces_valid:
+            return self._faces_aux
+        nbytes = int(lib.tt_face_aux_grid_bytes(_lib.i3(self.shape), self._par))
+        fa = getattr(self, "_faces_aux", None)
+        if fa is None or fa.numel() * 4 != nbytes:
+            self._faces_aux = None
+            if self.face_grid == "auto" and nbytes + (8 << 30) > torch.cuda.mem_get_info()[0]:
+                return None
+            self._faces_aux = torch.empty(nbytes // 4, dtype=torch.float32, device="cuda")
+        _lib.check(lib.tt_build_face_aux_grid(_lib.ptr(self._grid), _lib.ptr(aux4), _lib.i3(self.shape), _lib.d3(self._spacing),
+                                              self._par, _lib.ptr(self._faces_aux), _lib.stream_ptr()), "tt_build_face_aux_grid")
+        self._faces_aux_key = key
+        return self._faces_aux
 
     def _require_grid(self):
         if self._grid is None:
@@ -496,14 +519,22 @@ class ElectronCube:
         if use_aux:
             ap = _lib.AuxParams(float(self.omega), float(self.nc), float(self.VerdetConst))
             aux4 = self._aux_grid()
-        faces = None
-        applies = (nodes is None and not use_aux and grid.dtype == torch.float32 and self.steps_per_cell == 1
-                   and p.variant == 0)
+        faces = faces_aux = None
+        applies = (nodes is None and grid.dtype == torch.float32 and self.steps_per_cell == 1 and p.variant == 0)
         if self.face_grid is True and not applies:
-            raise ValueError("face_grid=True needs float32, uniformly spaced axes, steps_per_cell=1 and no B_on / "
-                             "inv_brems / phaseshift")
+            raise ValueError("face_grid=True needs float32, uniformly spaced axes and steps_per_cell=1")
         if self.face_grid and applies:
-            faces = self._face_grid()
+            if use_aux:                         # both face grids or neither (the aux grid is built behind the gradient faces)
+                had = self._faces is not None and self._faces_valid
+                faces = self._face_grid()
+                if faces is not None:
+                    if not had:
+                        self._faces_aux_key = None
+                    faces_aux = self._face_aux_grid(aux4)
+                    if faces_aux is None:
+                        faces = None
+            else:
+                faces = self._face_grid()
         steps = torch.zeros(1, dtype=torch.int64, device="cuda")
         events = getattr(self, "_trace_events", None)     # optional CUDA-event timing of the kernel
 
@@ -527,6 +558,11 @@ class ElectronCube:
                 _lib.check(lib.tt_trace_axes(C.byref(p), *(_lib.ptr(a) for a in nodes), _lib.ptr(grid), _lib.ptr(s0b), n,
                                              _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(steps),
                                              _lib.ptr(status), stream), "tt_trace_axes")
+            elif use_aux and faces_aux is not None:
+                _lib.check(lib.tt_trace_faces_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(faces),
+                                                  _lib.ptr(faces_aux), _lib.ptr(s0b), n, _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf),
+                                                  _lib.ptr(aux_out), _lib.ptr(steps), _lib.ptr(status), stream),
+                           "tt_trace_faces_aux")
             elif use_aux:
                 _lib.check(lib.tt_trace_aux(C.byref(p), C.byref(ap), _lib.ptr(grid), _lib.ptr(aux4), _lib.ptr(s0b), n,
                                             _lib.ptr(perm), _lib.ptr(rf), _lib.ptr(sf), _lib.ptr(aux_out),
