@@ -403,6 +403,19 @@ template <> TT_HD float trcp<float>(float x) {
 template <> TT_HD double trcp<double>(double x) { return 1.0 / x; }
 
 
+// sqrt(x) for x in (0, 1] as x * rsqrt(x): MUFU.RSQ + one multiplication (2 ulp) instead of the IEEE sequence (MUFU.RSQ,
+// two Newton steps, a slow-path branch: ~12 instructions, four times per step)
+TT_HD float tsqrt01(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return x * r;
+#else
+    return x / sqrtf(x);                                // host run of the kernel source (tests/host/)
+#endif
+}
+
+
 struct AuxArgs {
     double omega_over_c;    // phase = omega/c * int (n - 1) ds
     double verdet_nc;       // rotation = V * nc * int (ne/nc) (B . d) ds

@@ -363,8 +363,8 @@ TT_HD void trip_primed(TriP& q, float n00, float n10, float n01, float n11) {
 // two more packed polynomials, and the RK4 stages double as Simpson nodes of the three line integrals.
 TT_HD void aux_integrands(float nn, f32x2 bxy, f32x2 bzk, f32x2 duv, float dw, float hq, bool has_b,
                                                float& fp, float& ff, float& fa) {
-    const float r = sqrtf(fmaxf(1.f - nn, 0.f));
-    fp = -nn / (1.f + r) * hq;                      // (sqrt(1 - ne/nc) - 1) ds, without cancellation
+    const float r = tsqrt01(fmaxf(1.f - nn, 1e-30f));             // (MUFU.RSQ / MUFU.RCP: the IEEE square root and division
+    fp = -nn * trcp<float>(1.f + r) * hq;                          //  were ~20 instructions per stage)  (sqrt(1 - ne/nc) - 1) ds
     ff = 0.f; fa = 0.f;
     if (has_b) {
         const float bd = fmaf(lo2(bxy), lo2(duv), fmaf(hi2(bxy), hi2(duv), lo2(bzk) * dw));

@@ -108,18 +108,6 @@ TT_HD FaceA face_a_at(const FaceA& base, const FaceA& primed, f32x2 FW) {
 }
 #undef TT_FA_EACH
 
-// sqrt(x) for x in (0, 1] as x * rsqrt(x): MUFU.RSQ + one multiplication (2 ulp) instead of the IEEE sequence (MUFU.RSQ,
-// two Newton steps, a slow-path branch: ~12 instructions, four times per step)
-TT_HD float tsqrt01(float x) {
-#ifdef __CUDA_ARCH__
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return x * r;
-#else
-    return x / sqrtf(x);                                // host run of the kernel source (tests/host/)
-#endif
-}
-
 // the three integrands at one stage, per unit w-fraction and WITHOUT h_w (q = 1 / e_w), ADDED with Simpson weight w to
 // the running sums of the step
 TT_HD void face_a_integrands(const FaceA& a, f32x2 tuv, f32x2 euv, float ew, float q, float w, float& sp, float& sf_, float& sa) {
