@@ -95,7 +95,7 @@ extern "C" int tt_h2d_pageable(void* dst_dev, const void* src_host, size_t bytes
     std::mutex issue;                              // serialises cudaMemcpyAsync + event record on the stream
     auto work = [&](int t) {
         if (cudaSetDevice(dev) != cudaSuccess) { failed = 1; return; }
-        for (size_t i = (size_t)t; i < pieces; i += (size_t)nthreads) {
+        for (size_t i = (size_t)t; i < pieces && !failed.load(); i += (size_t)nthreads) {
             const int slot = (int)(i % kSlots);
             const unsigned round = (unsigned)(i / kSlots);
             while (seq[slot].load(std::memory_order_acquire) != round) {
@@ -115,9 +115,17 @@ extern "C" int tt_h2d_pageable(void* dst_dev, const void* src_host, size_t bytes
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    try {
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    } catch (...) {                                // no thread to be had: the pieces of the missing workers would never come
+        failed = 2;
+    }
     work(0);
     for (auto& th : pool) th.join();
+    if (failed.load() == 2) {
+        set_error("tt_h2d_pageable: could not start the staging threads (TT_H2D_THREADS=1 stages on the calling thread)");
+        return TT_ERR_CUDA;
+    }
     if (failed.load()) return cuda_fail(cudaGetLastError(), "tt_h2d_pageable: staging copy failed");
     return TT_OK;
 }
