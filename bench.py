@@ -647,6 +647,14 @@ def run_gpu_arm(args, wl):
                                            "kernel_ms": dms, "algorithmic_bytes_per_ray": 32, "achieved": gbs, "peak": peak_hbm,
                                            "unit": "GB/s", "frac": gbs / peak_hbm, "peak_source": peak_src,
                                            "note": "CUDA events around the launch inside the timed region (rank 0)"}
+            try:
+                te = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["entries"].get(f"detector/{wl}/smem16")
+            except Exception:
+                te = None
+            if te:                                   # (the main record bins at the default bin_scale = 10)
+                roofline["detector_kernel"].update(traffic=te["dram_gb_per_launch"] * main["rays_per_rank"] / te["rays_per_launch"],
+                                                   traffic_unit="GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                                                   profile=te["profile"])
 
     # ---- sub-records (same machinery, fewer steps): strong scaling, configs[4] share, configs[1], configs[3], FP64, ... ----
     extra = {}
