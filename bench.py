@@ -355,6 +355,12 @@ def build_roofline(key, kern, steps_per_launch, kernel_ms, clocks, bytes_per_ste
         r["frac"] = ach / peak_slots
         r["note"] = ("achieved = FMA-pipe issue slots/s x 64 flop (a packed FP32x2 instruction holds the pipe for 2 slots); "
                      "frac = share of the FP32 pipe's issue cycles in use = ncu sm__pipe_fma_cycles_active")
+        om = e.get("operand_model")
+        if om and not stale:
+            # cycles per warp-step and sub-partition, live: kernel time x SM clock x (148 SMs x 4) / warp-steps
+            cyc = kernel_ms * 1e-3 * sm_mhz * 1e6 * 148 * 4 / (steps_per_launch / 32.0)
+            r["operand_bandwidth_model"] = {"cycles_per_warp_step_model": om["cycles_per_warp_step"], "cycles_per_warp_step_measured": cyc,
+                                            "frac": om["cycles_per_warp_step"] / cyc, "mix": om["mix"], "note": om["note"]}
     alg = steps_per_launch * bytes_per_step / (kernel_ms * 1e-3) / 1e9
     r["hbm_algorithmic"] = {"bound": "hbm", "achieved": alg, "peak": peak_hbm, "unit": "GB/s", "frac": alg / peak_hbm,
                             "algorithmic_bytes_per_ray_step": bytes_per_step, "peak_source": peak_src,
